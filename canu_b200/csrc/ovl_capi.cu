@@ -1,0 +1,258 @@
+//  ovl_capi.cu -- the C ABI of include/ovlb200.h over the CUDA pipeline.
+#include "ovl_ctx.h"
+
+#include <cstring>
+#include <cmath>
+
+static thread_local std::string g_last_error;
+void ovl_set_error(const std::string &msg) { g_last_error = msg; }
+
+int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_hash, float *upload_ms, float *encode_ms);
+int ovl_build_index(ovlb_ctx *c);
+int ovl_seed_ref_batch(ovlb_ctx *c);
+int ovl_extend_pairs(ovlb_ctx *c);
+int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
+                     const int32_t *seed_start, const int32_t *seed_offset, const int32_t *seed_len,
+                     int32_t *out7, int32_t *deltas, uint32_t delta_stride);
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ovl_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return OVLB_ERR_CUDA; } } while (0)
+
+struct EvT {
+  cudaEvent_t a, b; cudaStream_t s;
+  EvT(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+  float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); cudaEventDestroy(a); cudaEventDestroy(b); return ms; }
+};
+
+extern "C" {
+
+const char *ovlb_last_error(void) { return g_last_error.c_str(); }
+
+int ovlb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
+  if (!p || !out) { ovl_set_error("ovlb_create: null argument"); return OVLB_ERR_ARG; }
+  *out = nullptr;
+  if (p->kmer_len < 2 || p->kmer_len > 31) { ovl_set_error("ovlb_create: kmer_len must be in 2..31"); return OVLB_ERR_ARG; }
+  if (!p->edit_match_limit || p->n_edit_match_limit < 2) { ovl_set_error("ovlb_create: edit_match_limit table missing"); return OVLB_ERR_ARG; }
+  if (!(p->max_erate > 0.0) || p->max_erate >= 1.0) { ovl_set_error("ovlb_create: max_erate must be in (0,1)"); return OVLB_ERR_ARG; }
+  if (p->max_read_len == 0 || p->max_read_len > OVLB_MAX_READLEN) { ovl_set_error("ovlb_create: max_read_len must be in 1..AS_MAX_READLEN"); return OVLB_ERR_ARG; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    ovl_set_error("ovlb_create: no CUDA device available (this library has no CPU fallback)");
+    return OVLB_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { ovl_set_error("ovlb_create: bad device index"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(device));
+  ovlb_ctx *c = new ovlb_ctx();
+  c->device = device;
+  c->P = *p;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  c->mem_budget = p->device_mem_budget ? p->device_mem_budget : (uint64_t)(free_b * 0.8);
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc((void **)&c->d_eml, (size_t)p->n_edit_match_limit * 4));
+  CK(cudaMemcpy(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice));
+  c->P.edit_match_limit = nullptr;                     // caller's buffer is not retained
+  CK(cudaMalloc((void **)&c->d_counters, sizeof(DevCounters)));
+  CK(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  CK(cudaMalloc((void **)&c->d_work, 64));
+  CK(cudaMemset(c->d_work, 0, 64));
+  c->dp.K = (int)p->kmer_len;
+  c->dp.partial = p->partial; c->dp.unique = p->unique_per_pair; c->dp.min_olap_len = p->min_olap_len;
+  c->dp.use_hopeless = p->use_hopeless_check;
+  c->dp.filter_by_kmer_count = p->filter_by_kmer_count;
+  c->dp.erate = p->max_erate; c->dp.bmv = p->branch_match_value; c->dp.min_tail_slope = p->min_branch_tail_slope;
+  c->dp.minkmers_factor = p->minkmers_exp_factor;
+  c->dp.eml = c->d_eml; c->dp.n_eml = p->n_edit_match_limit;
+  memset(&c->timings, 0, sizeof(c->timings));
+  *out = c;
+  return OVLB_OK;
+}
+
+static void free_reads(DevReads &d) {
+  void *ptrs[] = { d.fwd, d.rc, d.woff, d.len, d.pbase, d.flags, d.grp_read };
+  for (void *p : ptrs) if (p) cudaFree(p);
+  d = DevReads();
+}
+
+void ovlb_destroy(ovlb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_reads(c->hash); free_reads(c->ref);
+  void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.keys, c->index.cnt, c->index.start, c->index.occ, c->index.slot_of,
+                   c->ext.arena, c->ext.row_left, c->ext.row_off, c->ext.gring, c->ext.path, c->ext.ival, c->ext.ikc, c->ext.ldelta, c->ext.rdelta,
+                   c->d_packed, c->d_boff, c->d_nread, c->d_npos, c->ref_slot, c->ref_valid,
+                   c->run_key, c->run_val, c->run_key2, c->run_val2, c->runs_extra, c->pair_flag, c->pair_idx, c->cub_temp, c->pairs,
+                   c->seed_start, c->seed_off, c->seed_len, c->sim_nxt, c->sim_hits, c->sim_act, c->sim_order, c->seed_alive, c->d_records };
+  for (void *p : ptrs) if (p) cudaFree(p);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int ovlb_load_hash_reads(ovlb_ctx *c, const ovlb_reads *reads) {
+  if (!c || !reads) { ovl_set_error("ovlb_load_hash_reads: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  c->index.built = false;
+  c->skip_keys.clear();
+  return ovl_upload_reads(c, reads, c->hash, true, &c->timings.upload_ms, &c->timings.encode_ms);
+}
+
+int ovlb_mark_skip_kmers(ovlb_ctx *c, const uint64_t *keys, uint64_t n) {
+  if (!c || (n && !keys)) { ovl_set_error("ovlb_mark_skip_kmers: null argument"); return OVLB_ERR_ARG; }
+  if (c->index.built) { ovl_set_error("ovlb_mark_skip_kmers: must be called before ovlb_build_index"); return OVLB_ERR_STATE; }
+  const uint64_t lim = 1ull << (2 * c->P.kmer_len);
+  for (uint64_t i = 0; i < n; i++) {
+    if (keys[i] >= lim) { ovl_set_error("ovlb_mark_skip_kmers: key wider than 2*kmer_len bits"); return OVLB_ERR_ARG; }
+    c->skip_keys.push_back(keys[i]);
+  }
+  return OVLB_OK;
+}
+
+int ovlb_build_index(ovlb_ctx *c) {
+  if (!c) { ovl_set_error("ovlb_build_index: null context"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (c->hash.fwd == nullptr && c->hash.n == 0 && c->hash.cap_reads == 0) { ovl_set_error("ovlb_build_index: no hash reads loaded"); return OVLB_ERR_STATE; }
+  return ovl_build_index(c);
+}
+
+int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
+  if (!c || !reads) { ovl_set_error("ovlb_stage_ref_batch: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (!c->index.built) { ovl_set_error("ovlb_stage_ref_batch: build the index first"); return OVLB_ERR_STATE; }
+  c->staged = false;
+  int rc = ovl_upload_reads(c, reads, c->ref, false, &c->timings.upload_ms, &c->timings.encode_ms);
+  if (rc) return rc;
+  c->staged = true;
+  return OVLB_OK;
+}
+
+int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
+  if (!c) { ovl_set_error("ovlb_run_staged: null context"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (!c->staged) { ovl_set_error("ovlb_run_staged: no staged ref batch"); return OVLB_ERR_STATE; }
+  EvT tt(c->stream);
+  c->n_records = 0;
+  int rc = ovl_seed_ref_batch(c);
+  if (rc) { tt.stop(); return rc; }
+  EvT te(c->stream);
+  rc = ovl_extend_pairs(c);
+  if (rc) { te.stop(); tt.stop(); return rc; }
+  unsigned long long w[4] = {0, 0, 0, 0}, flags = 0;
+  CK(cudaMemcpyAsync(w, c->d_work, 32, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&flags, &c->d_counters->v[CT_ERR_FLAGS], 8, cudaMemcpyDeviceToHost, c->stream));
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  c->timings.extend_ms = te.stop();
+  c->timings.total_ms = tt.stop();
+  if (e != cudaSuccess) { ovl_set_error(std::string("extension kernel failed: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; }
+  if (flags) {
+    cudaMemset(&c->d_counters->v[CT_ERR_FLAGS], 0, 8);
+    ovl_set_error("device buffer overflow in the extension kernel (flags " + std::to_string(flags) + ")");
+    return OVLB_ERR_CAPACITY;
+  }
+  c->n_records = c->n_pairs ? w[2] : 0;
+  if (n_records) *n_records = c->n_records;
+  return OVLB_OK;
+}
+
+int ovlb_fetch_records(ovlb_ctx *c, ovlb_record *out, uint64_t out_cap, uint64_t *n_out) {
+  if (!c || !n_out) { ovl_set_error("ovlb_fetch_records: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  *n_out = c->n_records;
+  if (c->n_records > out_cap) { ovl_set_error("ovlb_fetch_records: output buffer too small"); return OVLB_ERR_CAPACITY; }
+  if (c->n_records && !out) { ovl_set_error("ovlb_fetch_records: null output"); return OVLB_ERR_ARG; }
+  EvT t(c->stream);
+  if (c->n_records) CK(cudaMemcpyAsync(out, c->d_records, c->n_records * sizeof(ovlb_record), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->timings.download_ms = t.stop();
+  return OVLB_OK;
+}
+
+int ovlb_overlap_ref_batch(ovlb_ctx *c, const ovlb_reads *reads, ovlb_record *out, uint64_t out_cap, uint64_t *n_out) {
+  int rc = ovlb_stage_ref_batch(c, reads);
+  if (rc) return rc;
+  uint64_t n = 0;
+  rc = ovlb_run_staged(c, &n);
+  if (rc) return rc;
+  return ovlb_fetch_records(c, out, out_cap, n_out);
+}
+
+int ovlb_get_counters(ovlb_ctx *c, ovlb_counters *out) {
+  if (!c || !out) { ovl_set_error("ovlb_get_counters: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  DevCounters h;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+  out->kmer_hits_without_olap = h.v[CT_HITS_WITHOUT]; out->kmer_hits_with_olap = h.v[CT_HITS_WITH];
+  out->kmer_hits_skipped = h.v[CT_HITS_SKIPPED]; out->multi_overlap = h.v[CT_MULTI];
+  out->total_overlaps = h.v[CT_TOTAL]; out->contained = h.v[CT_CONTAINED]; out->dovetail = h.v[CT_DOVETAIL];
+  out->extend_calls = h.v[CT_EXT_CALLS]; out->dp_cells = h.v[CT_DP_CELLS]; out->hash_kmers = h.v[CT_HASH_KMERS];
+  out->ref_kmers = h.v[CT_REF_KMERS]; out->seed_hits = h.v[CT_SEED_HITS]; out->seed_runs = h.v[CT_SEED_RUNS];
+  out->pairs = h.v[CT_PAIRS];
+  return OVLB_OK;
+}
+
+int ovlb_reset_counters(ovlb_ctx *c) {
+  if (!c) { ovl_set_error("ovlb_reset_counters: null context"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  return OVLB_OK;
+}
+
+int ovlb_get_timings(ovlb_ctx *c, ovlb_timings *out) {
+  if (!c || !out) { ovl_set_error("ovlb_get_timings: null argument"); return OVLB_ERR_ARG; }
+  *out = c->timings;
+  return OVLB_OK;
+}
+
+uint64_t ovlb_kernel_launches(ovlb_ctx *c) { return c ? c->launches : 0; }
+
+int ovlb_debug_pairs(ovlb_ctx *c, ovlb_pair_info *pairs, uint64_t pair_cap, uint64_t *n_pairs,
+                     ovlb_seed *seeds, uint64_t seed_cap, uint64_t *n_seeds) {
+  if (!c || !n_pairs || !n_seeds) { ovl_set_error("ovlb_debug_pairs: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  *n_pairs = c->n_pairs; *n_seeds = c->n_runs;
+  if (c->n_pairs > pair_cap || c->n_runs > seed_cap) { ovl_set_error("ovlb_debug_pairs: buffers too small"); return OVLB_ERR_CAPACITY; }
+  if (c->n_pairs == 0) return OVLB_OK;
+  std::vector<PairRec> hp(c->n_pairs);
+  std::vector<int32_t> s0(c->n_runs), s1(c->n_runs), s2(c->n_runs);
+  CK(cudaMemcpy(hp.data(), c->pairs, c->n_pairs * sizeof(PairRec), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(s0.data(), c->seed_start, c->n_runs * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(s1.data(), c->seed_off, c->n_runs * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(s2.data(), c->seed_len, c->n_runs * 4, cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < c->n_pairs; i++) {
+    const PairRec &p = hp[i];
+    int64_t end = (i + 1 < c->n_pairs) ? hp[i + 1].seed_begin : (int64_t)c->n_runs;
+    pairs[i].ref_id = c->ref.first_id + p.ref_idx; pairs[i].hash_id = c->hash.first_id + p.hash_idx;
+    pairs[i].dir = p.dir; pairs[i].consistent = p.consistent;
+    pairs[i].diag_ct = p.diag_ct; pairs[i].diag_bgn = p.diag_bgn; pairs[i].diag_end = p.diag_end;
+    pairs[i].n_seeds = (int32_t)(end - p.seed_begin);     // all seeds, even if the pair was dropped before extension
+    pairs[i].seed_begin = p.seed_begin;
+    if (p.n_seeds == 0) pairs[i].consistent |= 0x100;     // marker: dropped (hopeless / --minkmers)
+  }
+  for (uint64_t i = 0; i < c->n_runs; i++) { seeds[i].start = s0[i]; seeds[i].offset = s1[i]; seeds[i].len = s2[i]; }
+  return OVLB_OK;
+}
+
+int ovlb_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
+                      const int32_t *seed_start, const int32_t *seed_offset, const int32_t *seed_len,
+                      int32_t *out7, int32_t *deltas, uint32_t delta_stride) {
+  if (!c || !ref_index || !dir || !hash_index || !seed_start || !seed_offset || !seed_len || !out7) { ovl_set_error("ovlb_debug_extend: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (!c->staged) { ovl_set_error("ovlb_debug_extend: stage a ref batch first"); return OVLB_ERR_STATE; }
+  if (n == 0) return OVLB_OK;
+  return ovl_debug_extend(c, n, ref_index, dir, hash_index, seed_start, seed_offset, seed_len, out7, deltas, delta_stride);
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+//  ovl_ctx.h -- device-side data structures of one ovl context and the kernel launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ovlb200.h"
+#include "ovl_common.cuh"
+
+//  A set of reads resident in HBM (one for the hash block, one for the ref batch).
+struct DevReads {
+  uint32_t  n = 0;
+  uint32_t  first_id = 0;
+  uint64_t  total_bases = 0;
+  uint64_t  n_words = 0;          // dp4 words (incl. padding)
+  uint64_t  n_pos = 0;            // 32-aligned position index space (sum of round_up(len,32))
+  uint32_t  max_len = 0;
+  uint64_t *fwd = nullptr;        // dp4, forward
+  uint64_t *rc  = nullptr;        // dp4, reverse complement
+  uint64_t *woff = nullptr;       // [n] first word of read i
+  uint32_t *len = nullptr;        // [n]
+  uint64_t *pbase = nullptr;      // [n+1] first position index of read i (multiple of 32)
+  uint32_t *flags = nullptr;      // hash set: [n] bit0 lfrag_end_screened, bit1 rfrag_end_screened
+                                  // ref  set: [2n] per (read,dir): bit0 left_end_screened, bit1 right_end_screened
+  uint32_t *grp_read = nullptr;   // [n_pos/32] read index of each 32-position group
+  size_t    cap_words = 0, cap_reads = 0, cap_groups = 0;
+};
+
+//  The k-mer index over the hash block: open-addressed (linear probing) table of distinct k-mers,
+//  each with the contiguous list of its occurrences (CSR).
+struct DevIndex {
+  uint64_t  cap = 0;              // slots, power of two
+  uint64_t *keys = nullptr;       // [cap] k-mer (base j in bits 2j..2j+1) or OVL_EMPTY_KEY
+  uint32_t *cnt = nullptr;        // [cap] occurrences | OVL_SKIP_FLAG
+  uint32_t *start = nullptr;      // [cap] first entry in occ[]
+  uint64_t *occ = nullptr;        // [n_occ] (hash read index << 32) | offset
+  uint32_t *slot_of = nullptr;    // [hash n_pos] slot of the k-mer starting at each position (build scratch)
+  uint64_t  n_occ = 0;
+  bool      built = false;
+  size_t    cap_alloc = 0, occ_alloc = 0, slot_alloc = 0;
+};
+
+struct DevCounters {              // mirrors ovlb_counters; device-resident, atomically updated
+  unsigned long long v[16];
+};
+enum {
+  CT_HITS_WITHOUT = 0, CT_HITS_WITH, CT_HITS_SKIPPED, CT_MULTI, CT_TOTAL, CT_CONTAINED, CT_DOVETAIL,
+  CT_EXT_CALLS, CT_DP_CELLS, CT_HASH_KMERS, CT_REF_KMERS, CT_SEED_HITS, CT_SEED_RUNS, CT_PAIRS,
+  CT_ERR_FLAGS /* bit0: run buffer overflow, bit1: record overflow, bit2: arena overflow */,
+  CT_N
+};
+
+struct DevParams {                // kernel-visible job parameters
+  int       K;
+  int       partial, unique, min_olap_len, use_hopeless;
+  unsigned long long filter_by_kmer_count;
+  double    erate, bmv, min_tail_slope, minkmers_factor;
+  const int32_t *eml;             // Edit_Match_Limit
+  uint32_t  n_eml;
+};
+
+//  Per-warp scratch of the extension kernel.
+struct ExtScratch {
+  int       n_warps = 0;
+  int       emax = 0;             // max Error_Limit this scratch supports
+  uint64_t  arena_cap = 0;        // uint2 entries per warp
+  uint32_t  gring_cap = 0;        // ints per global ring (power of two)
+  uint2    *arena = nullptr;      // [n_warps][arena_cap]   from-code bit planes
+  int32_t  *row_left = nullptr;   // [n_warps][emax+2]
+  uint32_t *row_off = nullptr;    // [n_warps][emax+2]
+  int32_t  *gring = nullptr;      // [n_warps][2][gring_cap]
+  uint8_t  *path = nullptr;       // [n_warps][emax+2]
+  int32_t  *ival = nullptr;       // [n_warps][emax+2]
+  uint32_t *ikc = nullptr;        // [n_warps][emax+2]
+  int32_t  *ldelta = nullptr;     // [n_warps][emax+2]
+  int32_t  *rdelta = nullptr;     // [n_warps][emax+2]
+};
+
+struct PairRec {                  // one oriented candidate pair after chaining
+  uint32_t ref_idx, hash_idx;
+  int32_t  dir, consistent;
+  int32_t  diag_ct, diag_bgn, diag_end;
+  int32_t  n_seeds;               // 0 when the pair was dropped (hopeless / --minkmers)
+  int64_t  seed_begin;
+};
+
+struct ovlb_ctx {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  ovlb_params  P;
+  DevParams    dp;
+  int32_t     *d_eml = nullptr;
+  DevReads     hash, ref;
+  DevIndex     index;
+  DevCounters *d_counters = nullptr;
+  ExtScratch   ext;
+  uint64_t     mem_budget = 0;
+  int          sm_count = 148;
+
+  //  staging
+  uint8_t  *d_packed = nullptr;   size_t packed_cap = 0;
+  uint64_t *d_boff = nullptr;     size_t boff_cap = 0;
+  uint32_t *d_nread = nullptr, *d_npos = nullptr; size_t nn_cap = 0;
+  uint8_t  *h_pinned = nullptr;   size_t pinned_cap = 0;
+  std::vector<uint64_t> skip_keys;
+
+  //  lookup products for the current ref batch
+  int32_t  *ref_slot = nullptr;   size_t ref_slot_cap = 0;    // [2 * ref.n_pos] slot or -1
+  uint32_t *ref_valid = nullptr;  size_t ref_valid_cap = 0;   // [2 * ref.n_pos / 32] bit set iff slot >= 0
+  uint64_t *run_key = nullptr, *run_val = nullptr, *run_key2 = nullptr, *run_val2 = nullptr;
+  uint64_t  run_cap = 0;
+  OvlRun   *runs_extra = nullptr; size_t runs_extra_cap = 0;
+  uint64_t  n_runs = 0;
+  uint32_t *pair_flag = nullptr, *pair_idx = nullptr;
+  void     *cub_temp = nullptr;   size_t cub_temp_cap = 0;
+  PairRec  *pairs = nullptr;      uint64_t pair_cap = 0, n_pairs = 0;
+  int32_t  *seed_start = nullptr, *seed_off = nullptr, *seed_len = nullptr;   // [n_runs] list order per pair
+  int32_t  *sim_nxt = nullptr, *sim_hits = nullptr, *sim_act = nullptr, *sim_order = nullptr;
+  uint8_t  *seed_alive = nullptr;
+  uint64_t  seed_cap = 0;
+  ovlb_record *d_records = nullptr;  uint64_t rec_cap = 0;  uint64_t n_records = 0;
+  unsigned long long *d_work = nullptr;   // persistent-kernel work counters
+
+  ovlb_timings timings;
+  uint64_t     launches = 0;
+  bool         staged = false;
+};
+
+//  launchers (each returns cudaError_t of the launch; all on ctx->stream)
+void ovl_set_error(const std::string &msg);

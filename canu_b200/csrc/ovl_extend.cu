@@ -1,0 +1,772 @@
+//  ovl_extend.cu -- K4/K5: warp-per-candidate-pair banded prefix-edit-distance extension.
+//
+//  Replaces, bit-exactly (paths under /root/reference/src/overlapInCore):
+//    Process_Matches                     overlapInCore-Process_String_Overlaps.C:355-547
+//    Extend_Alignment                    liboverlap/prefixEditDistance-extend.C:36-183
+//    prefixEditDistance::forward/reverse liboverlap/prefixEditDistance-forward.C:94-314, -reverse.C:114-330
+//    Set_Right_Delta / Set_Left_Delta    -forward.C:32-71, -reverse.C:36-93
+//    Add_Overlap, Combine_Into_One_Olap, Merge_Intersecting_Olaps, Choose_Best_Partial,
+//    Lies_On_Alignment                   Process_String_Overlaps.C:42-311
+//    Output_Overlap / Output_Partial_Overlap   overlapInCore-Output.C:27-264
+//
+//  Design.  One warp owns one oriented read pair.  The O(ND) edit array is computed one error row
+//  at a time; lanes stride the diagonals of the row.  Only the previous and the current row are
+//  kept (shared-memory rings indexed by diagonal modulo the ring size; a per-warp ring in HBM takes
+//  over for bands wider than the shared ring).  For the traceback the reference keeps the whole
+//  triangle of int32 cells; we keep 2 bits per cell ("from" code: 0 = same diagonal/mismatch,
+//  1 = from d-1, 2 = from d+1, decided with the reference's tie order) as two ballot bit-planes per
+//  32 cells in a per-warp HBM arena, walk the path back through the codes, then re-slide forward
+//  along the path to recover the row values the delta encoding needs.  The reverse extension runs
+//  the same forward code on the reverse-complemented copies of both reads.
+//
+//  Integer DP: no tensor cores.  The only floating point is the branch-point score, evaluated once
+//  per row in FP64 with separate multiply and subtract (the reference build has no FMA).
+#include "ovl_ctx.h"
+
+#define EXT_WARPS  8
+#define EXT_THREADS (EXT_WARPS * 32)
+#define SRING      1024                   // ints per shared ring (per row, per warp)
+#define FULL       0xffffffffu
+
+struct WarpMem {
+  int      *sring0, *sring1;              // shared rings
+  int      *gring0, *gring1;              // HBM rings
+  uint32_t  gring_cap;
+  uint2    *arena;  uint64_t arena_cap;
+  int32_t  *row_left; uint32_t *row_off;
+  uint8_t  *path; int32_t *ival; uint32_t *ikc;
+  int32_t  *ldelta, *rdelta;
+  int       emax;
+};
+
+struct DpOut { int a_end, t_end, errors, leftover, match_to_end, delta_len; };
+
+//  Number of leading positions (< lim) where A[a..] and T[t..] match; all 32 lanes cooperate, 512 bases per round.
+__device__ __forceinline__ int warp_slide(const uint64_t *A, int a, const uint64_t *T, int t, int lim, int lane) {
+  int total = 0;
+  while (total < lim) {
+    int pos = total + 16 * lane;
+    int k = 0;
+    if (pos < lim) k = ovl_match16(ovl_fetch16(A, a + pos), ovl_fetch16(T, t + pos));
+    unsigned nf = __ballot_sync(FULL, k < 16);
+    if (nf == 0) { total += 512; continue; }
+    int first = __ffs(nf) - 1;
+    int kk = __shfl_sync(FULL, k, first);
+    total += 16 * first + kk;
+    break;
+  }
+  return total < lim ? total : lim;
+}
+
+//  i-th value pushed by Set_Right_Delta / Set_Left_Delta's loop (k descending): V_i = row value below indel i.
+__device__ __forceinline__ int push_at(const WarpMem &M, int i, int v_start) {
+  int vi = M.ival[i];
+  int vp = (i == 0) ? v_start : M.ival[i - 1];
+  return ((M.ikc[i] >> 30) == 1u) ? (vi - vp - 1) : (vp - vi);
+}
+
+//  Traceback through the from-codes, then delta encoding.  Returns delta_len; writes deltas to `out`.
+//  fwd_rules: Set_Right_Delta conventions; else Set_Left_Delta (sets leftover, may bump t_mag).
+__device__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+                              int e_start, int d_start, int v_start, int row0, bool fwd_rules,
+                              int32_t *out, int &leftover, int &t_mag, int lane) {
+  //  Phase A: walk down, 32 rows per round
+  int n_ind = 0;
+  int dcur = d_start;
+  for (int kb = e_start; kb >= 1; kb -= 32) {
+    const int kk = kb - lane;                      // my row
+    int rl = 0; uint32_t glo = 0; uint2 w0 = make_uint2(0, 0), w1 = w0, w2 = w0;
+    if (kk >= 1) {
+      rl = M.row_left[kk];
+      uint32_t ro = M.row_off[kk];
+      int idx_lo = dcur - lane - rl; if (idx_lo < 0) idx_lo = 0;
+      glo = (uint32_t)idx_lo >> 5;
+      const uint2 *ap = M.arena + ro + glo;
+      w0 = ap[0]; w1 = ap[1]; w2 = ap[2];
+    }
+    int mycode = 0;
+    const int steps = kb < 32 ? kb : 32;
+    for (int l = 0; l < steps; l++) {
+      int rl_l = __shfl_sync(FULL, rl, l);
+      uint32_t glo_l = __shfl_sync(FULL, glo, l);
+      int idx = dcur - rl_l;
+      int gi = (idx >> 5) - (int)glo_l;
+      unsigned x0 = gi == 0 ? w0.x : (gi == 1 ? w1.x : w2.x);
+      unsigned y0 = gi == 0 ? w0.y : (gi == 1 ? w1.y : w2.y);
+      unsigned x = __shfl_sync(FULL, x0, l), y = __shfl_sync(FULL, y0, l);
+      //  note: gi computed from the broadcast (uniform) values, so every lane selects the same word index
+      int bit = idx & 31;
+      int code = ((x >> bit) & 1) | (((y >> bit) & 1) << 1);
+      if (lane == l) mycode = code;
+      if (code == 1) dcur--; else if (code == 2) dcur++;
+    }
+    if (kk >= 1) M.path[kk] = (uint8_t)mycode;
+    unsigned im = __ballot_sync(FULL, kk >= 1 && mycode != 0);
+    if (kk >= 1 && mycode != 0) {
+      int idx = n_ind + __popc(im & ((1u << lane) - 1));
+      M.ikc[idx] = (uint32_t)kk | ((uint32_t)mycode << 30);
+    }
+    n_ind += __popc(im);
+  }
+  __syncwarp();
+
+  //  Phase B: re-slide upward to recover v_{k-1} at every indel step k
+  if (n_ind > 0) {
+    int v = row0, d = 0, seen = 0;
+    for (int kb = 1; kb <= e_start; kb += 32) {
+      int myc = 0;
+      if (kb + lane <= e_start) myc = M.path[kb + lane];
+      const int steps = (e_start - kb + 1) < 32 ? (e_start - kb + 1) : 32;
+      for (int l = 0; l < steps; l++) {
+        const int k = kb + l;
+        const int c = __shfl_sync(FULL, myc, l);
+        if (c != 0) {
+          if (lane == 0) M.ival[n_ind - 1 - seen] = v;
+          seen++;
+        }
+        if (k == e_start || seen == n_ind) { kb = e_start + 1; break; }   // nothing above the last indel is needed
+        d += (c == 1) ? 1 : ((c == 2) ? -1 : 0);
+        int pre = (c == 1) ? v : v + 1;
+        int lim = min(m - pre, n - d - pre);
+        v = pre + warp_slide(A, a0 + pre, T, t0 + pre + d, lim, lane);
+      }
+    }
+  }
+  __syncwarp();
+
+  //  Phase C: deltas.  push_i = (code 1) ? V_i - V_{i-1} - 1 : V_{i-1} - V_i, with V_{-1} = v_start.
+  const int last = n_ind ? M.ival[n_ind - 1] : v_start;
+#define PUSH(i) push_at(M, (i), v_start)
+  int len = n_ind;
+  if (fwd_rules) {
+    //  stack S[0..n_ind-1] = pushes, S[n_ind] = last+1;  Right_Delta[j] = |S[n_ind-j]| * sign(S[n_ind-j-1])
+    for (int j = lane; j < n_ind; j += 32) {
+      int i = n_ind - j;
+      int si  = (i == n_ind) ? (last + 1) : PUSH(i);
+      int sim = PUSH(i - 1);
+      int a = si < 0 ? -si : si;
+      out[j] = a * ((sim > 0) - (sim < 0));
+    }
+  } else {
+    leftover = last;
+    bool fix = false;
+    if (n_ind > 1) {
+      int p0 = PUSH(0);
+      fix = (p0 == 1) && (t_mag < n);                 // Left_Delta[0] == 1 && t_end + t_len > 0
+    }
+    if (fix) {
+      for (int j = lane; j < n_ind - 1; j += 32) {
+        int pj = PUSH(j + 1);
+        out[j] = (j == 0) ? ((pj > 0) ? pj + 1 : pj - 1) : pj;
+      }
+      len = n_ind - 1;
+      t_mag += 1;
+    } else {
+      for (int j = lane; j < n_ind; j += 32) out[j] = PUSH(j);
+    }
+  }
+#undef PUSH
+  __syncwarp();
+  return len;
+}
+
+//  One banded extension (forward(), or reverse() on reverse-complemented strings).
+//  A: shorter string (m <= n), starting at base a0 of the dp4 words A; T likewise.
+__device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+                        int error_limit, bool fwd_rules, int32_t *delta_out, DpOut &o,
+                        unsigned long long &cells, unsigned long long &calls, unsigned long long *err_flags, int lane) {
+  o.leftover = 0; o.delta_len = 0;
+  int row0 = warp_slide(A, a0, T, t0, m, lane);
+  if (row0 == m) {                                   // exact match to the end of A
+    o.a_end = m; o.t_end = m; o.leftover = m; o.match_to_end = 1; o.errors = 0;
+    return;
+  }
+  calls++;
+
+  int *prev = M.sring0, *cur = M.sring1;
+  uint32_t mask = SRING - 1;
+  bool in_shared = true;
+  if (lane == 0) prev[0] = row0;
+  int L = 0, R = 0;
+  int longest = 0, best_d = 0, best_e = 0;
+  int ms_len = 0, ms_d = 0, ms_e = 0;
+  double max_score = 0.0;
+  uint32_t aoff = 0;
+  const double bmv = P.bmv;
+  int e;
+  __syncwarp();
+
+  for (e = 1; e <= error_limit; e++) {
+    const int Lu = L - 1, Ru = R + 1;
+    const int width = Ru - Lu + 1;
+    if (in_shared && width + 4 > SRING) {            // migrate the previous row to the HBM ring
+      for (int d = L + lane; d <= R; d += 32) M.gring0[d & (M.gring_cap - 1)] = prev[d & mask];
+      __syncwarp();
+      prev = M.gring0; cur = M.gring1; mask = M.gring_cap - 1; in_shared = false;
+    }
+    const uint32_t ngroups = (uint32_t)(width + 31) >> 5;
+    if ((!in_shared && (uint32_t)(width + 4) > M.gring_cap) || (uint64_t)aoff + ngroups + 4 > M.arena_cap || e > M.emax) {
+      if (lane == 0) atomicOr(err_flags, 4ull);       // scratch too small: reported as an error by the host
+      break;
+    }
+    if (lane == 0) {
+      prev[(L - 1) & mask] = -2; prev[(L - 2) & mask] = -2; prev[(R + 1) & mask] = -2; prev[(R + 2) & mask] = -2;
+      M.row_left[e] = Lu; M.row_off[e] = aoff;
+    }
+    __syncwarp();
+
+    int term_d = 0x7fffffff, term_row = 0;
+    for (uint32_t g = 0; g < ngroups; g++) {
+      const int d = Lu + (int)(g << 5) + lane;
+      const bool act = d <= Ru;
+      int row = 0, code = 0;
+      if (act) {
+        int a = prev[(d - 1) & mask], b = prev[d & mask], c2 = prev[(d + 1) & mask];
+        row = 1 + b;
+        if (a > row) { row = a; code = 1; }
+        if (1 + c2 > row) { row = 1 + c2; code = 2; }
+        int lim = min(m - row, n - d - row);
+        int cnt = 0;
+        while (cnt < lim) {
+          int k = ovl_match16(ovl_fetch16(A, a0 + row + cnt), ovl_fetch16(T, t0 + row + d + cnt));
+          cnt += k;
+          if (k < 16) break;
+        }
+        row += (cnt < lim ? cnt : lim);
+        cur[d & mask] = row;
+      }
+      unsigned b0 = __ballot_sync(FULL, act && (code & 1));
+      unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
+      if (lane == 0) M.arena[aoff + g] = make_uint2(b0, b1);
+      unsigned hb = __ballot_sync(FULL, act && (row == m || row + d == n));
+      if (hb) {
+        int tl = __ffs(hb) - 1;
+        term_d = Lu + (int)(g << 5) + tl;
+        term_row = __shfl_sync(FULL, row, tl);
+        break;
+      }
+    }
+    __syncwarp();
+
+    if (term_d != 0x7fffffff) {
+      cells += (unsigned long long)(term_d - Lu + 1);
+      //  reached the end of A or T: branch-point test (forward.C:170-212)
+      double score = __dsub_rn(__dmul_rn((double)term_row, bmv), (double)e);
+      int tail_len = term_row - ms_len;
+      bool abort_ = false;
+      if (P.partial && score < max_score) abort_ = true;
+      if (e > OVL_MIN_BRANCH_END_DIST / 2 && tail_len >= OVL_MIN_BRANCH_END_DIST) {
+        double slope = __ddiv_rn(__dsub_rn(max_score, score), (double)tail_len);
+        if (slope >= P.min_tail_slope) abort_ = true;
+      }
+      if (abort_) {
+        o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
+        o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules,
+                                     delta_out, o.leftover, o.t_end, lane);
+        return;
+      }
+      int d = term_d;
+      if (fwd_rules && term_row == m && d < Ru && 1 + prev[(d + 1) & mask] == term_row) d++;   // force last error to be a mismatch
+      o.a_end = term_row; o.t_end = term_row + d; o.match_to_end = 1; o.errors = e;
+      o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, e, d, term_row, row0, fwd_rules, delta_out, o.leftover, o.t_end, lane);
+      return;
+    }
+    cells += (unsigned long long)width;
+    aoff += ngroups;
+
+    //  prune the band edges (forward.C:245-280): P(d) = EA[e][d] + max(d,0) < Edit_Match_Limit[e]
+    const int lim_e = P.eml[e];
+    int mn = 0x7fffffff, mx = -0x7fffffff;
+    for (int d = Lu + lane; d <= Ru; d += 32) {
+      int v = cur[d & mask];
+      if (!(v + (d > 0 ? d : 0) < lim_e)) { mn = min(mn, d); mx = max(mx, d); }
+    }
+    mn = __reduce_min_sync(FULL, mn);
+    mx = __reduce_max_sync(FULL, mx);
+    if (mn > mx) break;                               // Left > Right
+    L = mn; R = mx;
+
+    int bv = -1, bd = 0x7fffffff;
+    for (int d = L + lane; d <= R; d += 32) {
+      int v = cur[d & mask];
+      if (v > bv) { bv = v; bd = d; }
+    }
+    int vmax = __reduce_max_sync(FULL, bv);
+    int dmin = __reduce_min_sync(FULL, bv == vmax ? bd : 0x7fffffff);
+    if (vmax > longest) { longest = vmax; best_d = dmin; best_e = e; }
+
+    double score = __dsub_rn(__dmul_rn((double)longest, bmv), (double)e);
+    if (score > max_score) { max_score = score; ms_len = longest; ms_d = best_d; ms_e = best_e; }
+
+    int *t = prev; prev = cur; cur = t;
+    __syncwarp();
+  }
+
+  //  error limit exhausted or band closed
+  o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
+  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules,
+                               delta_out, o.leftover, o.t_end, lane);
+}
+
+struct ReadView {
+  const uint64_t *fwd, *rc;     // dp4 words of this read, forward and reverse complement
+  int len;
+};
+
+//  Extend_Alignment (prefixEditDistance-extend.C:36-183).  S is the ref read in its search orientation
+//  (S.fwd = oriented sequence, S.rc = its reverse complement); T the hash read.
+//  On return M.ldelta[0..ldelta_len) is the merged Left_Delta.
+__device__ int warp_extend_alignment(const DevParams &P, WarpMem &M, const ReadView &S, const ReadView &T,
+                                     int m_start, int m_offset, int m_len,
+                                     int &s_lo, int &s_hi, int &t_lo, int &t_hi, int &errors, int &ldelta_len,
+                                     unsigned long long &cells, unsigned long long &calls, unsigned long long *err_flags, int lane) {
+  int right_errors = 0, left_errors = 0, leftover = 0;
+  bool r_to_end = true, l_to_end = true;
+  const int s_left_begin = m_start - 1, s_right_begin = m_start + m_len, s_right_len = S.len - s_right_begin;
+  const int t_left_begin = m_offset - 1, t_right_begin = m_offset + m_len, t_right_len = T.len - t_right_begin;
+  const int total_olap = min(m_start, m_offset) + m_len + min(s_right_len, t_right_len);
+  const int error_limit = (int)ceil(__dmul_rn((double)total_olap, P.erate));      // Error_Bound[Total_Olap]
+
+  int rlen = 0, llen = 0;
+  bool r_negate = false, l_negate = false;
+  DpOut o;
+
+  if (s_right_len == 0 || t_right_len == 0) {
+    s_hi = 0; t_hi = 0;
+  } else if (s_right_len <= t_right_len) {
+    warp_dp(P, M, S.fwd, s_right_begin, s_right_len, T.fwd, t_right_begin, t_right_len, error_limit, true, M.rdelta, o, cells, calls, err_flags, lane);
+    right_errors = o.errors; s_hi = o.a_end; t_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len; r_negate = true;
+  } else {
+    warp_dp(P, M, T.fwd, t_right_begin, t_right_len, S.fwd, s_right_begin, s_right_len, error_limit, true, M.rdelta, o, cells, calls, err_flags, lane);
+    right_errors = o.errors; t_hi = o.a_end; s_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len;
+  }
+  s_hi += s_right_begin - 1;
+  t_hi += t_right_begin - 1;
+
+  if (s_left_begin < 0 || t_left_begin < 0) {
+    s_lo = 0; t_lo = 0;
+  } else if (s_right_begin <= t_right_begin) {
+    //  reverse(S + s_left_begin, ...) == forward on the reverse complements, starting at the mirrored position
+    warp_dp(P, M, S.rc, S.len - 1 - s_left_begin, s_left_begin + 1, T.rc, T.len - 1 - t_left_begin, t_left_begin + 1,
+            error_limit - right_errors, false, M.ldelta, o, cells, calls, err_flags, lane);
+    left_errors = o.errors; s_lo = -o.a_end; t_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
+  } else {
+    warp_dp(P, M, T.rc, T.len - 1 - t_left_begin, t_left_begin + 1, S.rc, S.len - 1 - s_left_begin, s_left_begin + 1,
+            error_limit - right_errors, false, M.ldelta, o, cells, calls, err_flags, lane);
+    left_errors = o.errors; t_lo = -o.a_end; s_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
+    l_negate = true;
+  }
+  s_lo += s_left_begin + 1;
+  t_lo += t_left_begin + 1;
+  errors = left_errors + right_errors;
+
+  const int kind = !r_to_end ? (!l_to_end ? OVL_NONE : OVL_RIGHT_BRANCH_PT) : (!l_to_end ? OVL_LEFT_BRANCH_PT : OVL_DOVETAIL);
+
+  //  merge: Left_Delta (sign-flipped when T played "A"), then the right deltas, negated (extend.C:164-175)
+  __syncwarp();
+  if (l_negate) for (int i = lane; i < llen; i += 32) M.ldelta[i] = -M.ldelta[i];
+  for (int i = lane; i < rlen; i += 32) {
+    int rd = M.rdelta[i]; if (r_negate) rd = -rd;
+    int v;
+    if (i == 0) v = (rd > 0) ? -(rd + leftover + m_len) : -(rd - leftover - m_len);
+    else        v = -rd;
+    M.ldelta[llen + i] = v;
+  }
+  ldelta_len = llen + rlen;
+  __syncwarp();
+  return kind;
+}
+
+//  Lies_On_Alignment (Process_String_Overlaps.C:262-281); each lane walks the shared delta list for its own seed.
+__device__ __forceinline__ bool lies_on_alignment(const int32_t *ld, int ld_len, int start, int offset, int s_lo, int t_lo) {
+  int diag = t_lo - s_lo, new_diag = offset - start;
+  for (int i = 0; i < ld_len; i++) {
+    int dl = ld[i];
+    s_lo += dl < 0 ? -dl : dl;
+    if (start < s_lo) break;
+    if (dl < 0) diag++;
+    else { s_lo++; diag--; }
+  }
+  int x = new_diag - diag; if (x < 0) x = -x;
+  return x <= OVL_SHIFT_SLACK;
+}
+
+//  Add_Overlap (Process_String_Overlaps.C:177-244)
+__device__ void add_overlap(const DevParams &P, int s_lo, int s_hi, int t_lo, int t_hi, double qual, int delta_ct, OvlOlap *o, int &ct) {
+  if (!P.partial) {
+    int new_diag = t_lo - s_lo;
+    for (int i = 0; i < ct; i++) {
+      int old_diag = o[i].t_lo - o[i].s_lo;
+      if ((new_diag >  0 && old_diag >  0 && o[i].t_right_boundary - new_diag - o[i].s_left_boundary >= OVL_MIN_INTERSECTION) ||
+          (new_diag <= 0 && old_diag <= 0 && o[i].s_right_boundary + new_diag - o[i].t_left_boundary >= OVL_MIN_INTERSECTION)) {
+        if (new_diag < o[i].min_diag) o[i].min_diag = new_diag;
+        if (new_diag > o[i].max_diag) o[i].max_diag = new_diag;
+        if (s_lo < o[i].s_left_boundary)  o[i].s_left_boundary  = s_lo;
+        if (s_hi > o[i].s_right_boundary) o[i].s_right_boundary = s_hi;
+        if (t_lo < o[i].t_left_boundary)  o[i].t_left_boundary  = t_lo;
+        if (t_hi > o[i].t_right_boundary) o[i].t_right_boundary = t_hi;
+        if (qual < o[i].quality) {
+          o[i].s_lo = s_lo; o[i].s_hi = s_hi; o[i].t_lo = t_lo; o[i].t_hi = t_hi;
+          o[i].quality = qual; o[i].delta_ct = delta_ct;
+        }
+        return;
+      }
+    }
+  }
+  if (ct >= OVL_MAX_DISTINCT_OLAPS) return;
+  OvlOlap &n = o[ct];
+  n.s_lo = n.s_left_boundary  = s_lo;  n.s_hi = n.s_right_boundary = s_hi;
+  n.t_lo = n.t_left_boundary  = t_lo;  n.t_hi = n.t_right_boundary = t_hi;
+  n.quality = qual; n.delta_ct = delta_ct;
+  n.min_diag = n.max_diag = t_lo - s_lo;
+  ct++;
+}
+
+__device__ void combine_into_one(OvlOlap *o, int ct, int *deleted) {            // :42-96
+  int best = 0;
+  int min_diag = o[0].min_diag, max_diag = o[0].max_diag;
+  int slb = o[0].s_left_boundary, srb = o[0].s_right_boundary, tlb = o[0].t_left_boundary, trb = o[0].t_right_boundary;
+  for (int i = 1; i < ct; i++) {
+    int leni = 1 + min(o[i].s_hi - o[i].s_lo, o[i].t_hi - o[i].t_lo);
+    int lenb = 1 + min(o[best].s_hi - o[best].s_lo, o[best].t_hi - o[best].t_lo);
+    if (o[i].quality < o[best].quality || (o[i].quality == o[best].quality && leni > lenb)) best = i;
+    min_diag = min(min_diag, o[i].min_diag); max_diag = max(max_diag, o[i].max_diag);
+    slb = min(slb, o[i].s_left_boundary); srb = max(srb, o[i].s_right_boundary);
+    tlb = min(tlb, o[i].t_left_boundary); trb = max(trb, o[i].t_right_boundary);
+  }
+  o[best].min_diag = min_diag; o[best].max_diag = max_diag;
+  o[best].s_left_boundary = slb; o[best].s_right_boundary = srb; o[best].t_left_boundary = tlb; o[best].t_right_boundary = trb;
+  for (int i = 0; i < ct; i++) deleted[i] = (i != best);
+}
+
+__device__ void merge_intersecting(OvlOlap *p, int ct, int *deleted) {          // :108-162
+  for (int i = 0; i < ct - 1; i++)
+    for (int j = i + 1; j < ct; j++) {
+      if (deleted[i] || deleted[j]) continue;
+      int lo_diag = p[i].min_diag, hi_diag = p[i].max_diag;
+      if ((lo_diag <= 0 && p[j].min_diag > 0) || (lo_diag > 0 && p[j].min_diag <= 0)) continue;
+      if ((lo_diag >= 0 && p[j].t_right_boundary - lo_diag - p[j].s_left_boundary >= OVL_MIN_INTERSECTION) ||
+          (lo_diag <= 0 && p[j].s_right_boundary + lo_diag - p[j].t_left_boundary >= OVL_MIN_INTERSECTION) ||
+          (hi_diag >= 0 && p[j].t_right_boundary - hi_diag - p[j].s_left_boundary >= OVL_MIN_INTERSECTION) ||
+          (hi_diag <= 0 && p[j].s_right_boundary + hi_diag - p[j].t_left_boundary >= OVL_MIN_INTERSECTION)) {
+        int keep, disc;
+        if (p[i].quality < p[j].quality) { keep = i; disc = j; deleted[j] = 1; }
+        else                             { keep = j; disc = i; deleted[i] = 1; }
+        p[keep].min_diag = min(p[keep].min_diag, p[disc].min_diag);
+        p[keep].max_diag = max(p[keep].max_diag, p[disc].max_diag);
+        p[keep].s_left_boundary  = min(p[keep].s_left_boundary,  p[disc].s_left_boundary);
+        p[keep].s_right_boundary = max(p[keep].s_right_boundary, p[disc].s_right_boundary);
+        p[keep].t_left_boundary  = min(p[keep].t_left_boundary,  p[disc].t_left_boundary);
+        p[keep].t_right_boundary = max(p[keep].t_right_boundary, p[disc].t_right_boundary);
+      }
+    }
+}
+
+__device__ void choose_best_partial(OvlOlap *o, int ct, int *deleted) {         // :291-311
+  int best = 0;
+  double mbest = __dmul_rn(__dsub_rn(1.0, o[0].quality), (double)(2 + o[0].s_hi - o[0].s_lo + o[0].t_hi - o[0].t_lo));
+  for (int i = 1; i < ct; i++) {
+    double mb = __dmul_rn(__dsub_rn(1.0, o[i].quality), (double)(2 + o[i].s_hi - o[i].s_lo + o[i].t_hi - o[i].t_lo));
+    if (mbest < mb || (mbest == mb && o[i].quality < o[best].quality)) best = i;
+  }
+  for (int i = 0; i < ct; i++) deleted[i] = (i != best);
+}
+
+__device__ __forceinline__ void bind_warp_mem(WarpMem &M, const ExtScratch &X, int *sm, int warp_in_block, int gwarp) {
+  M.sring0 = sm + (size_t)warp_in_block * 2 * SRING;
+  M.sring1 = M.sring0 + SRING;
+  M.gring_cap = X.gring_cap;
+  M.gring0 = X.gring + (size_t)gwarp * 2 * X.gring_cap;
+  M.gring1 = M.gring0 + X.gring_cap;
+  M.arena = X.arena + (size_t)gwarp * X.arena_cap;  M.arena_cap = X.arena_cap;
+  const size_t st = (size_t)X.emax + 2;
+  M.row_left = X.row_left + gwarp * st;  M.row_off = X.row_off + gwarp * st;
+  M.path = X.path + gwarp * st;  M.ival = X.ival + gwarp * st;  M.ikc = X.ikc + gwarp * st;
+  M.ldelta = X.ldelta + gwarp * st;  M.rdelta = X.rdelta + gwarp * st;
+  M.emax = X.emax;
+}
+
+//  Persistent kernel: warps pull pairs from a global cursor (pairs differ wildly in cost).
+__global__ void __launch_bounds__(EXT_THREADS)
+k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uint64_t n_pairs,
+               const int32_t *__restrict__ seed_start, const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_len,
+               uint8_t *seed_alive,
+               const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff,
+               const uint32_t *__restrict__ rlen, uint32_t ref_first_id,
+               const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hrc, const uint64_t *__restrict__ hwoff,
+               const uint32_t *__restrict__ hlen, uint32_t hash_first_id,
+               ovlb_record *records, uint64_t rec_cap, unsigned long long *work, unsigned long long *counters) {
+  extern __shared__ int sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * EXT_WARPS + wib;
+  if (gwarp >= X.n_warps) return;
+  WarpMem M;
+  bind_warp_mem(M, X, sm, wib, gwarp);
+
+  unsigned long long cells = 0, calls = 0, c_with = 0, c_without = 0, c_multi = 0, c_total = 0, c_cont = 0, c_dove = 0;
+  unsigned long long *err_flags = &counters[CT_ERR_FLAGS];
+
+  while (true) {
+    unsigned long long pi = 0;
+    if (lane == 0) pi = atomicAdd(&work[1], 1ull);
+    pi = __shfl_sync(FULL, pi, 0);
+    if (pi >= n_pairs) break;
+    const PairRec pr = pairs[pi];
+    if (pr.n_seeds == 0) continue;
+
+    ReadView S, T;
+    S.len = (int)rlen[pr.ref_idx];
+    S.fwd = (pr.dir ? rrc : rfwd) + rwoff[pr.ref_idx];
+    S.rc  = (pr.dir ? rfwd : rrc) + rwoff[pr.ref_idx];
+    T.len = (int)hlen[pr.hash_idx];
+    T.fwd = hfwd + hwoff[pr.hash_idx];
+    T.rc  = hrc + hwoff[pr.hash_idx];
+    const uint32_t s_id = ref_first_id + pr.ref_idx, t_id = hash_first_id + pr.hash_idx;
+    const int64_t sb = pr.seed_begin;
+    const int ns = pr.n_seeds;
+
+    OvlOlap distinct[OVL_MAX_DISTINCT_OLAPS];
+    int distinct_ct = 0;
+    int remaining = ns;
+
+    while (remaining > 0) {
+      //  longest seed, first in list order on ties (Process_String_Overlaps.C:424-431)
+      unsigned long long best = 0;
+      for (int i = lane; i < ns; i += 32)
+        if (seed_alive[sb + i]) {
+          unsigned long long key = ((unsigned long long)(uint32_t)seed_len[sb + i] << 32) | (uint32_t)(0x7fffffff - i);
+          if (key > best) best = key;
+        }
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { unsigned long long x = __shfl_xor_sync(FULL, best, o); if (x > best) best = x; }
+      const int li = 0x7fffffff - (int)(uint32_t)best;
+      const int m_start = seed_start[sb + li], m_offset = seed_off[sb + li], m_len = seed_len[sb + li];
+
+      int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
+      const int kind = warp_extend_alignment(P, M, S, T, m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len,
+                                             cells, calls, err_flags, lane);
+
+      const bool usable = (kind == OVL_DOVETAIL) || P.partial;
+      if (usable && 1 + s_hi - s_lo >= P.min_olap_len && 1 + t_hi - t_lo >= P.min_olap_len) {
+        int olap_len = 1 + min(s_hi - s_lo, t_hi - t_lo);
+        double quality = __ddiv_rn((double)errors, (double)olap_len);
+        if (errors <= (int)ceil(__dmul_rn((double)olap_len, P.erate)))
+          add_overlap(P, s_lo, s_hi, t_lo, t_hi, quality, ld_len, distinct, distinct_ct);
+      }
+
+      if (pr.consistent) break;                       // all remaining seeds are dropped (:473-474)
+
+      //  remove the seed just used and every seed lying on the alignment (:476-490)
+      int removed = 0;
+      for (int i0 = 0; i0 < ns; i0 += 32) {
+        const int i = i0 + lane;
+        bool rm = false;
+        if (i < ns && seed_alive[sb + i]) {
+          if (i == li) rm = true;
+          else if (usable) {
+            int st = seed_start[sb + i], ln = seed_len[sb + i];
+            if (s_lo - OVL_SHIFT_SLACK <= st && st + ln <= (s_hi + 1) + OVL_SHIFT_SLACK - 1 &&
+                lies_on_alignment(M.ldelta, ld_len, st, seed_off[sb + i], s_lo, t_lo))
+              rm = true;
+          }
+          if (rm) seed_alive[sb + i] = 0;
+        }
+        removed += __popc(__ballot_sync(FULL, rm));
+      }
+      remaining -= removed;
+      __syncwarp();
+    }
+
+    int outputs = 0;
+    if (distinct_ct > 0) {
+      int deleted[OVL_MAX_DISTINCT_OLAPS] = {0, 0, 0};
+      if (P.partial) { if (P.unique) choose_best_partial(distinct, distinct_ct, deleted); }
+      else           { if (P.unique) combine_into_one(distinct, distinct_ct, deleted); else merge_intersecting(distinct, distinct_ct, deleted); }
+      for (int i = 0; i < distinct_ct; i++)
+        if (!deleted[i]) {
+          uint32_t a, b; uint64_t w0, w1;
+          if (P.partial) {
+            ovl_output_partial(s_id, t_id, pr.dir, distinct[i], S.len, T.len, &a, &b, &w0, &w1);
+          } else {
+            int cont = ovl_output_overlap(s_id, S.len, pr.dir, t_id, T.len, distinct[i], &a, &b, &w0, &w1);
+            if (cont) c_cont++; else c_dove++;
+          }
+          c_total++;
+          if (lane == 0) {
+            unsigned long long ri = atomicAdd(&work[2], 1ull);
+            if (ri < rec_cap) { ovlb_record r; r.a_iid = a; r.b_iid = b; r.dat0 = w0; r.dat1 = w1; records[ri] = r; }
+            else atomicOr(err_flags, 2ull);
+          }
+          outputs++;
+        }
+    }
+    if (outputs == 0) c_without++;
+    else { c_with++; if (outputs > 1) c_multi++; }
+  }
+
+  if (lane == 0) {
+    if (c_without) atomicAdd(&counters[CT_HITS_WITHOUT], c_without);
+    if (c_with)    atomicAdd(&counters[CT_HITS_WITH], c_with);
+    if (c_multi)   atomicAdd(&counters[CT_MULTI], c_multi);
+    if (c_total)   atomicAdd(&counters[CT_TOTAL], c_total);
+    if (c_cont)    atomicAdd(&counters[CT_CONTAINED], c_cont);
+    if (c_dove)    atomicAdd(&counters[CT_DOVETAIL], c_dove);
+    if (cells)     atomicAdd(&counters[CT_DP_CELLS], cells);
+    if (calls)     atomicAdd(&counters[CT_EXT_CALLS], calls);
+  }
+}
+
+//  Debug tap: one warp per explicit seed; out7 = s_lo, s_hi, t_lo, t_hi, errors, kind, delta_ct.
+__global__ void __launch_bounds__(EXT_THREADS)
+k_debug_extend(DevParams P, ExtScratch X, uint32_t n, const uint32_t *__restrict__ ref_index, const int32_t *__restrict__ dir,
+               const uint32_t *__restrict__ hash_index, const int32_t *__restrict__ m_start, const int32_t *__restrict__ m_offset,
+               const int32_t *__restrict__ m_len,
+               const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff, const uint32_t *__restrict__ rlen,
+               const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hrc, const uint64_t *__restrict__ hwoff, const uint32_t *__restrict__ hlen,
+               int32_t *out7, int32_t *deltas, uint32_t delta_stride, unsigned long long *work, unsigned long long *counters) {
+  extern __shared__ int sm[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * EXT_WARPS + wib;
+  if (gwarp >= X.n_warps) return;
+  WarpMem M;
+  bind_warp_mem(M, X, sm, wib, gwarp);
+  unsigned long long cells = 0, calls = 0;
+  while (true) {
+    unsigned long long i = 0;
+    if (lane == 0) i = atomicAdd(&work[1], 1ull);
+    i = __shfl_sync(FULL, i, 0);
+    if (i >= n) break;
+    ReadView S, T;
+    const uint32_t ri = ref_index[i], hi = hash_index[i];
+    const int dr = dir[i];
+    S.len = (int)rlen[ri]; S.fwd = (dr ? rrc : rfwd) + rwoff[ri]; S.rc = (dr ? rfwd : rrc) + rwoff[ri];
+    T.len = (int)hlen[hi]; T.fwd = hfwd + hwoff[hi]; T.rc = hrc + hwoff[hi];
+    int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
+    int kind = warp_extend_alignment(P, M, S, T, m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
+                                     cells, calls, &counters[CT_ERR_FLAGS], lane);
+    if (lane == 0) {
+      int32_t *o = out7 + 7 * i;
+      o[0] = s_lo; o[1] = s_hi; o[2] = t_lo; o[3] = t_hi; o[4] = errors; o[5] = kind; o[6] = ld_len;
+    }
+    if (deltas)
+      for (int j = lane; j < ld_len && j < (int)delta_stride; j += 32) deltas[(size_t)i * delta_stride + j] = M.ldelta[j];
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (cells) atomicAdd(&counters[CT_DP_CELLS], cells);
+    if (calls) atomicAdd(&counters[CT_EXT_CALLS], calls);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  host side
+// ------------------------------------------------------------------------------------------------
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ovl_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return OVLB_ERR_CUDA; } } while (0)
+
+static void free_ext(ExtScratch &X) {
+  void *ptrs[] = { X.arena, X.row_left, X.row_off, X.gring, X.path, X.ival, X.ikc, X.ldelta, X.rdelta };
+  for (void *p : ptrs) if (p) cudaFree(p);
+  X = ExtScratch();
+}
+
+//  Size the per-warp scratch for the longest read currently on the device.
+int ovl_prepare_ext_scratch(ovlb_ctx *c) {
+  uint32_t maxlen = c->hash.max_len > c->ref.max_len ? c->hash.max_len : c->ref.max_len;
+  if (maxlen < 64) maxlen = 64;
+  int emax = (int)ceil((double)maxlen * c->P.max_erate) + 2;          // Error_Limit <= Error_Bound[len] <= this
+  if ((uint32_t)emax + 1 > c->P.n_edit_match_limit) emax = (int)c->P.n_edit_match_limit - 1;
+  if (c->ext.arena && c->ext.emax >= emax) return OVLB_OK;
+  free_ext(c->ext);
+  ExtScratch X;
+  X.emax = emax;
+  //  worst-case code words of one extension: sum_e ceil((2e+1)/32) + slack
+  uint64_t worst = 0;
+  for (int e = 1; e <= emax; e++) worst += (uint64_t)(2 * e + 1 + 31) / 32;
+  X.arena_cap = worst + 64;
+  uint32_t gcap = 64; while (gcap < (uint32_t)(2 * emax + 16)) gcap <<= 1;
+  X.gring_cap = gcap;
+  const uint64_t per_warp = X.arena_cap * 8 + (uint64_t)gcap * 8 + (uint64_t)(emax + 2) * (4 + 4 + 1 + 4 + 4 + 4 + 4);
+  int want_warps = c->sm_count * 24;                                    // 3 CTAs of 8 warps per SM
+  uint64_t budget = c->mem_budget / 4;
+  if (per_warp * want_warps > budget) want_warps = (int)(budget / per_warp);
+  want_warps = (want_warps / EXT_WARPS) * EXT_WARPS;
+  if (want_warps < EXT_WARPS) { ovl_set_error("not enough device memory for the extension scratch (reads too long for the budget)"); return OVLB_ERR_CAPACITY; }
+  X.n_warps = want_warps;
+  const size_t st = (size_t)emax + 2;
+  CK(cudaMalloc((void **)&X.arena, (size_t)want_warps * X.arena_cap * sizeof(uint2)));
+  CK(cudaMalloc((void **)&X.gring, (size_t)want_warps * 2 * gcap * 4));
+  CK(cudaMalloc((void **)&X.row_left, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.row_off, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.path, want_warps * st));
+  CK(cudaMalloc((void **)&X.ival, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.ikc, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.ldelta, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.rdelta, want_warps * st * 4));
+  c->ext = X;
+  const int smem = EXT_WARPS * 2 * SRING * 4;
+  CK(cudaFuncSetAttribute(k_extend_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_debug_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return OVLB_OK;
+}
+
+int ovl_extend_pairs(ovlb_ctx *c) {
+  if (c->n_pairs == 0) return OVLB_OK;
+  int rc = ovl_prepare_ext_scratch(c);
+  if (rc) return rc;
+  //  records: at most 1 (unique) or MAX_DISTINCT_OLAPS per pair
+  uint64_t need = c->n_pairs * (c->P.unique_per_pair ? 1 : OVL_MAX_DISTINCT_OLAPS) + 16;
+  if (need > c->rec_cap) {
+    if (c->d_records) cudaFree(c->d_records); c->d_records = nullptr;
+    uint64_t want = need * 5 / 4;
+    CK(cudaMalloc((void **)&c->d_records, want * sizeof(ovlb_record)));
+    c->rec_cap = want;
+  }
+  const int smem = EXT_WARPS * 2 * SRING * 4;
+  int blocks = c->ext.n_warps / EXT_WARPS;
+  uint64_t need_blocks = (c->n_pairs + EXT_WARPS - 1) / EXT_WARPS;
+  if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
+  k_extend_pairs<<<blocks, EXT_THREADS, smem, c->stream>>>(
+      c->dp, c->ext, c->pairs, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive,
+      c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->ref.first_id,
+      c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len, c->hash.first_id,
+      c->d_records, c->rec_cap, c->d_work, c->d_counters->v);
+  c->launches++;
+  CK(cudaGetLastError());
+  return OVLB_OK;
+}
+
+int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
+                     const int32_t *seed_start, const int32_t *seed_offset, const int32_t *seed_len,
+                     int32_t *out7, int32_t *deltas, uint32_t delta_stride) {
+  int rc = ovl_prepare_ext_scratch(c);
+  if (rc) return rc;
+  uint32_t *d_u = nullptr; int32_t *d_i = nullptr, *d_out = nullptr, *d_del = nullptr;
+  CK(cudaMalloc((void **)&d_u, (size_t)n * 2 * 4));
+  CK(cudaMalloc((void **)&d_i, (size_t)n * 4 * 4));
+  CK(cudaMalloc((void **)&d_out, (size_t)n * 7 * 4));
+  if (deltas) { CK(cudaMalloc((void **)&d_del, (size_t)n * delta_stride * 4)); CK(cudaMemset(d_del, 0, (size_t)n * delta_stride * 4)); }
+  CK(cudaMemcpy(d_u, ref_index, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_u + n, hash_index, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_i, dir, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_i + n, seed_start, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_i + 2 * n, seed_offset, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_i + 3 * n, seed_len, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemsetAsync(c->d_work, 0, 64, c->stream));
+  const int smem = EXT_WARPS * 2 * SRING * 4;
+  int blocks = c->ext.n_warps / EXT_WARPS;
+  uint64_t need_blocks = ((uint64_t)n + EXT_WARPS - 1) / EXT_WARPS;
+  if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
+  k_debug_extend<<<blocks, EXT_THREADS, smem, c->stream>>>(
+      c->dp, c->ext, n, d_u, d_i, d_u + n, d_i + n, d_i + 2 * n, d_i + 3 * n,
+      c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len,
+      d_out, d_del, delta_stride, c->d_work, c->d_counters->v);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out7, d_out, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost));
+  if (deltas) CK(cudaMemcpy(deltas, d_del, (size_t)n * delta_stride * 4, cudaMemcpyDeviceToHost));
+  cudaFree(d_u); cudaFree(d_i); cudaFree(d_out); if (d_del) cudaFree(d_del);
+  return OVLB_OK;
+}

@@ -1,0 +1,187 @@
+//  ovl_host.cc -- host-only (no CUDA) helpers of the C ABI: parameter derivation and read packing.
+//
+//  Follows overlapInCore.C:380-411,454-459 (flag fix-ups), liboverlap/prefixEditDistance.C:23-107
+//  (MAX_ERRORS, slope, branch value) and liboverlap/Binomial_Bound.C:36-188 (Edit_Match_Limit).
+//  All of it is FP64 libm arithmetic whose results feed integer tables; it must be evaluated in the
+//  reference's operation order (and without FMA contraction: compiled with -ffp-contract=off).
+#include "../../include/ovlb200.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+void ovl_set_error(const std::string &msg);
+
+namespace {
+
+//  Smallest n >= start with P[at least e errors in n trials at rate p] > 1e-4  (Binomial_Bound.C:36-99).
+int binomial_bound(int e, double p, int start) {
+  const double kProbBound = 1e-4, kNormalZ = 3.62;
+  const double q = 1.0 - p;
+  if (start < e) start = e;
+  for (int n = start; n < (int)OVLB_MAX_READLEN; n++) {
+    if (n <= 35) {
+      double sum = 0.0, pp = 1.0, qq = pow(q, n);
+      int coeff = 1, ct = 0;
+      for (int k = 0; k < e && 1.0 - sum > kProbBound; k++) {
+        sum += coeff * pp * qq;
+        coeff *= n - ct;
+        coeff /= ++ct;
+        pp *= p;
+        qq /= q;
+      }
+      if (1.0 - sum > kProbBound) return n;
+    } else {
+      double z = (e - 0.5 - n * p) / sqrt(n * p * q);
+      if (z <= kNormalZ) return n;
+      double sum = 0.0, mu = 1.0, fact = 1.0, pc = exp(-n * p);
+      for (int k = 0; k < e; k++) {
+        sum += mu * pc / fact;
+        mu *= n * p;
+        fact *= k + 1;
+      }
+      if (1.0 - sum > kProbBound) return n;
+    }
+  }
+  return (int)OVLB_MAX_READLEN;
+}
+
+//  Initialize_Match_Limit (Binomial_Bound.C:104-188), AS_MAX_READLEN_BITS == 21 slope constants.
+void match_limit_table(int32_t *ml, double erate, int32_t max_errors) {
+  int32_t e = 0, s = 1;
+  const int32_t exact = max_errors < 2000 ? max_errors : 2000;
+  while (e <= 1) ml[e++] = 0;
+  for (; e < exact; e++) {
+    s = binomial_bound(e - 1, erate, s);
+    ml[e] = s - 1;
+  }
+  const double slope = 0.982064188397525 / erate + 0.067835741959926;
+  double v = ml[e - 1] + slope;
+  for (; e < max_errors; e++) {
+    ml[e] = (int32_t)ceil(v);
+    v += slope;
+  }
+}
+
+}  // namespace
+
+struct ovlb_reads_owner {
+  std::vector<uint8_t>  packed;
+  std::vector<uint64_t> boff;
+  std::vector<uint32_t> len, n_read, n_pos;
+  ovlb_reads view;
+};
+
+extern "C" {
+
+double ovlb_parse_erate(const char *text) { return (double)strtof(text, nullptr); }
+
+int ovlb_params_init(ovlb_params *p, uint32_t kmer_len, double max_erate, double align_noise,
+                     int partial, int unique_per_pair, int min_olap_len, int no_hopeless, int min_kmers,
+                     uint32_t max_read_len) {
+  if (!p) { ovl_set_error("ovlb_params_init: null"); return OVLB_ERR_ARG; }
+  if (kmer_len < 2 || kmer_len > 31) { ovl_set_error("ovlb_params_init: kmer_len must be in 2..31"); return OVLB_ERR_ARG; }
+  if (!(max_erate > 0.0) || max_erate >= 1.0) { ovl_set_error("ovlb_params_init: max_erate must be in (0,1)"); return OVLB_ERR_ARG; }
+  if (align_noise == 0.0) align_noise = 1.0;
+  memset(p, 0, sizeof(*p));
+  p->kmer_len = kmer_len;
+  p->partial = partial ? 1 : 0;
+  p->unique_per_pair = unique_per_pair ? 1 : 0;
+  p->min_olap_len = min_olap_len;
+  p->use_hopeless_check = no_hopeless ? 0 : 1;
+  if (max_erate > 0.06) p->use_hopeless_check = 0;
+  p->minkmers_exp_factor = exp(-1.0 * (double)kmer_len * max_erate);
+  p->filter_by_kmer_count = 0;
+  if (min_kmers) {
+    //  int(floor(exp(-K*erate) * (Min_Olap_Len - Kmer_Len + 1))), the subtraction done in uint64 (overlapInCore.C:411)
+    uint64_t span = (uint64_t)(int64_t)min_olap_len - (uint64_t)kmer_len + 1;
+    p->filter_by_kmer_count = (uint64_t)(int)floor(p->minkmers_exp_factor * (double)span);
+  }
+  p->max_erate = max_erate;
+  p->branch_match_value = max_erate / (1 + max_erate);
+  p->min_branch_tail_slope = (max_erate > 0.06) ? 1.0 : 0.20;
+  const uint32_t max_errors = 1 + (uint32_t)(int)ceil(max_erate * OVLB_MAX_READLEN);
+  int32_t *ml = (int32_t *)calloc((size_t)max_errors + 1, sizeof(int32_t));
+  if (!ml) { ovl_set_error("ovlb_params_init: out of memory"); return OVLB_ERR_ARG; }
+  match_limit_table(ml, max_erate * align_noise, (int32_t)max_errors);
+  p->edit_match_limit = ml;
+  p->n_edit_match_limit = max_errors;
+  p->max_read_len = max_read_len ? max_read_len : OVLB_MAX_READLEN;
+  p->device_mem_budget = 0;
+  return OVLB_OK;
+}
+
+void ovlb_params_free(ovlb_params *p) {
+  if (p && p->edit_match_limit) { free((void *)p->edit_match_limit); p->edit_match_limit = nullptr; }
+}
+
+int ovlb_pack_reads(const char *bases, const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads,
+                    uint32_t first_read_id, uint32_t min_len, ovlb_reads_owner **out) {
+  if (!out || (n_reads && (!bases || !offsets || !lens))) { ovl_set_error("ovlb_pack_reads: null argument"); return OVLB_ERR_ARG; }
+  ovlb_reads_owner *o = new ovlb_reads_owner();
+  o->boff.resize(n_reads); o->len.resize(n_reads);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_reads; i++) {
+    uint32_t L = lens[i] < min_len ? 0 : lens[i];
+    o->boff[i] = total; o->len[i] = L;
+    total += ((uint64_t)L + 3) / 4;
+  }
+  o->packed.assign(total + 8, 0);
+  for (uint32_t i = 0; i < n_reads; i++) {
+    const uint32_t L = o->len[i];
+    const char *s = bases + offsets[i];
+    uint8_t *dst = o->packed.data() + o->boff[i];
+    for (uint32_t j = 0; j < L; j++) {
+      unsigned code;
+      switch (s[j]) {
+        case 'A': case 'a': code = 0; break;
+        case 'C': case 'c': code = 1; break;
+        case 'G': case 'g': code = 2; break;
+        case 'T': case 't': code = 3; break;
+        case 'N': case 'n': code = 0; o->n_read.push_back(i); o->n_pos.push_back(j); break;
+        default:
+          delete o;
+          ovl_set_error("ovlb_pack_reads: read " + std::to_string(first_read_id + i) + " has a base that is not ACGTN at position " + std::to_string(j));
+          return OVLB_ERR_ARG;
+      }
+      dst[j >> 2] |= (uint8_t)(code << (6 - 2 * (j & 3)));
+    }
+  }
+  o->view.packed = o->packed.data();
+  o->view.packed_bytes = total;
+  o->view.byte_offset = o->boff.data();
+  o->view.len = o->len.data();
+  o->view.n_reads = n_reads;
+  o->view.first_read_id = first_read_id;
+  o->view.n_read = o->n_read.data();
+  o->view.n_pos = o->n_pos.data();
+  o->view.n_n = o->n_read.size();
+  *out = o;
+  return OVLB_OK;
+}
+
+const ovlb_reads *ovlb_reads_view(const ovlb_reads_owner *o) { return o ? &o->view : nullptr; }
+void ovlb_reads_free(ovlb_reads_owner *o) { delete o; }
+
+int ovlb_kmer_keys(const char *kmer, uint32_t kmer_len, uint64_t *fwd_key, uint64_t *rc_key) {
+  if (!kmer || !fwd_key || !rc_key || kmer_len < 2 || kmer_len > 31) { ovl_set_error("ovlb_kmer_keys: bad argument"); return OVLB_ERR_ARG; }
+  uint64_t f = 0, r = 0;
+  for (uint32_t j = 0; j < kmer_len; j++) {
+    uint64_t code;
+    switch (kmer[j]) {
+      case 'A': case 'a': code = 0; break;
+      case 'C': case 'c': code = 1; break;
+      case 'G': case 'g': code = 2; break;
+      case 'T': case 't': code = 3; break;
+      default: ovl_set_error("ovlb_kmer_keys: non-ACGT base in skip k-mer"); return OVLB_ERR_ARG;
+    }
+    f |= code << (2 * j);
+    r |= (3 - code) << (2 * (kmer_len - 1 - j));
+  }
+  *fwd_key = f; *rc_key = r;
+  return OVLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+/*
+ *  ovlb200.h -- C ABI of the B200-native `overlapInCore` (ovl) hot path.
+ *
+ *  This is the drop-in boundary: plain C, opaque handle, plain
+ *  pointers and sizes, no CUDA / torch types.  The C++ host driver
+ *  (canu_b200/host/, the `overlapInCore` replacement executable), the Python
+ *  ctypes binding (canu_b200/api.py) and a maintainer's binding inside Canu
+ *  itself all sit on these entry points.
+ *
+ *  Every call returns 0 on success and a negative code on failure;
+ *  ovlb_last_error() returns a human-readable message for the calling thread's
+ *  last failure.  No exceptions cross the boundary.  The caller owns all host
+ *  buffers.  A context is bound to one CUDA device and must be used by one host
+ *  thread at a time.  There is NO CPU fallback: without a usable CUDA device
+ *  ovlb_create() fails.
+ *
+ *  Reference interfaces replaced (paths under /root/reference/src/overlapInCore):
+ *
+ *    ovlb_params / ovlb_create        oicParameters G + prefixEditDistance ctor:
+ *                                     overlapInCore.H:367-473, overlapInCore.C:293-459,
+ *                                     liboverlap/prefixEditDistance.C:23-107
+ *    ovlb_load_hash_reads +           Build_Hash_Index():
+ *      ovlb_mark_skip_kmers +           overlapInCore-Build_Hash_Index.C:415-631 (build),
+ *      ovlb_build_index                 :186-257 (Mark_Skip_Kmers)
+ *    ovlb_overlap_ref_batch           Process_Overlaps() -> Find_Overlaps() ->
+ *                                     Process_String_Olaps() -> Process_Matches() ->
+ *                                     prefixEditDistance::Extend_Alignment() ->
+ *                                     Output_Overlap()/Output_Partial_Overlap():
+ *                                     overlapInCore-Process_Overlaps.C:25-122,
+ *                                     overlapInCore-Find_Overlaps.C:235-336,
+ *                                     overlapInCore-Process_String_Overlaps.C:355-690,
+ *                                     liboverlap/prefixEditDistance-extend.C:36-183,
+ *                                     overlapInCore-Output.C:27-264
+ *    ovlb_record                      ovOverlap (a_iid, b_iid, ovOverlapDAT):
+ *                                     ../stores/ovOverlap.H:49-78,279-291
+ *    ovlb_counters                    the -s statistics: overlapInCore.C:550-558
+ */
+#ifndef OVLB200_H
+#define OVLB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVLB_MAX_READLEN_BITS 21                       /* AS_MAX_READLEN_BITS, ../stores/sqStore.H:57 */
+#define OVLB_MAX_READLEN      ((1u << OVLB_MAX_READLEN_BITS) - 1)
+
+/* error codes */
+#define OVLB_OK              0
+#define OVLB_ERR_ARG        -1     /* bad argument */
+#define OVLB_ERR_CUDA       -2     /* CUDA runtime / kernel failure, or no device */
+#define OVLB_ERR_CAPACITY   -3     /* a device buffer overflowed; split the batch and retry */
+#define OVLB_ERR_STATE      -4     /* call sequence violated */
+
+typedef struct ovlb_ctx ovlb_ctx;
+
+/*  Parameters of one overlap job.  All tables are computed on the HOST exactly
+ *  as the reference computes them (they inherit float-parsed error rates and
+ *  libm results) and uploaded at create time.  */
+typedef struct {
+  uint32_t       kmer_len;              /* G.Kmer_Len, 1..31                                   */
+  int32_t        partial;               /* G.Doing_Partial_Overlaps (-partial)                 */
+  int32_t        unique_per_pair;       /* G.Unique_Olap_Per_Pair (-u default 1, -m 0)         */
+  int32_t        min_olap_len;          /* G.Min_Olap_Len (--minlength)                        */
+  int32_t        use_hopeless_check;    /* G.Use_Hopeless_Check after the erate>0.06 / -z fix-up */
+  uint64_t       filter_by_kmer_count;  /* G.Filter_By_Kmer_Count after overlapInCore.C:410-411; 0 = off */
+  double         max_erate;             /* G.maxErate as a double (already rounded via strtof) */
+  double         branch_match_value;    /* maxErate / (1 + maxErate)                           */
+  double         min_branch_tail_slope; /* 1.0 if maxErate > 0.06 else 0.20                    */
+  double         minkmers_exp_factor;   /* exp(-K * maxErate): computeExpected()'s constant    */
+  const int32_t *edit_match_limit;      /* Edit_Match_Limit[0 .. n_edit_match_limit)           */
+  uint32_t       n_edit_match_limit;    /* MAX_ERRORS                                          */
+  uint32_t       max_read_len;          /* longest read that will ever be loaded (sizes scratch) */
+  uint64_t       device_mem_budget;     /* bytes of HBM this context may use; 0 = 80% of free  */
+} ovlb_params;
+
+/*  A set of reads handed to the device: 2-bit packed bases exactly as sqStore
+ *  stores them (4 bases per byte, first base in the two MOST significant bits;
+ *  A=0 C=1 G=2 T=3; utility/src/sequence/sequence-v1.C:268-351), each read
+ *  starting on a byte boundary at byte_offset[i].  Non-ACGT bases ('N') are
+ *  packed as A and listed separately as (read index, position) pairs.  A read
+ *  with len 0 is absent (deleted / too short / filtered by library) but keeps
+ *  its slot so that read ID = first_read_id + index.  */
+typedef struct {
+  const uint8_t  *packed;               /* packed bases of all reads                           */
+  uint64_t        packed_bytes;
+  const uint64_t *byte_offset;          /* [n_reads]                                           */
+  const uint32_t *len;                  /* [n_reads] bases                                     */
+  uint32_t        n_reads;
+  uint32_t        first_read_id;        /* ID of reads[0]                                      */
+  const uint32_t *n_read;               /* [n_n] read index of each N                          */
+  const uint32_t *n_pos;                /* [n_n] position of each N                            */
+  uint64_t        n_n;
+} ovlb_reads;
+
+/*  One overlap, bit-identical to the reference's in-memory ovOverlap
+ *  (24 bytes: a_iid, b_iid, dat[0], dat[1]).  */
+typedef struct {
+  uint32_t a_iid, b_iid;
+  uint64_t dat0;   /* ahg5:21 | ahg3:21 | evalue:16 | flipped | forOBT | forDUP | forUTG | 2 spare (LSB first) */
+  uint64_t dat1;   /* bhg5:21 | bhg3:21 | span:21 | 1 spare                                                  */
+} ovlb_record;
+
+/*  Statistics; the first seven are the reference's counters, the rest are the
+ *  measurement counters of SURVEY.md 8d.  All are cumulative over the context's
+ *  life until ovlb_reset_counters().  */
+typedef struct {
+  uint64_t kmer_hits_without_olap;
+  uint64_t kmer_hits_with_olap;
+  uint64_t kmer_hits_skipped;
+  uint64_t multi_overlap;
+  uint64_t total_overlaps;
+  uint64_t contained;
+  uint64_t dovetail;
+  uint64_t extend_calls;      /* forward/reverse extensions that ran a DP                     */
+  uint64_t dp_cells;          /* DP cells, counted as the reference evaluates them            */
+  uint64_t hash_kmers;        /* k-mers inserted into the index                               */
+  uint64_t ref_kmers;         /* ref windows looked up (both orientations)                    */
+  uint64_t seed_hits;         /* exact k-mer hits (Add_Ref calls in the reference)            */
+  uint64_t seed_runs;         /* maximal diagonal runs those hits collapse into               */
+  uint64_t pairs;             /* oriented candidate read pairs                                */
+} ovlb_counters;
+
+/*  Per-stage device times of the last ovlb_build_index / ovlb_overlap_ref_batch
+ *  call, in milliseconds, measured with CUDA events on the context's stream.  */
+typedef struct {
+  float upload_ms, encode_ms;
+  float index_count_ms, index_scan_ms, index_fill_ms, index_skip_ms;
+  float probe_ms, expand_ms, sort_ms, chain_ms, extend_ms, download_ms;
+  float total_ms;
+} ovlb_timings;
+
+const char *ovlb_last_error(void);
+int  ovlb_device_count(void);
+
+int  ovlb_create(int device, const ovlb_params *params, ovlb_ctx **out);
+void ovlb_destroy(ovlb_ctx *ctx);
+
+/*  Hash side.  load -> (mark skip k-mers)* -> build.  Loading replaces any
+ *  previous block.  skip keys: k-mer with base j in bits [2j, 2j+1] (A0 C1 G2 T3),
+ *  BOTH orientations must be supplied by the caller (Build_Hash_Index.C:226-243).  */
+int  ovlb_load_hash_reads(ovlb_ctx *ctx, const ovlb_reads *reads);
+int  ovlb_mark_skip_kmers(ovlb_ctx *ctx, const uint64_t *keys, uint64_t n);
+int  ovlb_build_index(ovlb_ctx *ctx);
+
+/*  Ref side: overlap every read of the batch, in both orientations, against the
+ *  current hash block (only pairs with refID < hashID are computed,
+ *  Find_Overlaps.C:279,320).  Records are written to out[0..*n_out); if more than
+ *  out_cap are produced the call fails with OVLB_ERR_CAPACITY and *n_out holds
+ *  the required capacity.  Record order is unspecified (as in the reference).  */
+int  ovlb_overlap_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads,
+                            ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
+
+/*  Same, but for benchmarking with inputs resident in HBM: stage a batch once,
+ *  then run the device pipeline repeatedly without host<->device copies.  */
+int  ovlb_stage_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads);
+int  ovlb_run_staged(ovlb_ctx *ctx, uint64_t *n_records);
+int  ovlb_fetch_records(ovlb_ctx *ctx, ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
+
+int  ovlb_get_counters(ovlb_ctx *ctx, ovlb_counters *out);
+int  ovlb_reset_counters(ovlb_ctx *ctx);
+int  ovlb_get_timings(ovlb_ctx *ctx, ovlb_timings *out);
+uint64_t ovlb_kernel_launches(ovlb_ctx *ctx);   /* kernels launched by this context so far */
+
+/*  Kernel-granularity debug taps used by the parity tests (tests/ only).  After
+ *  ovlb_run_staged()/ovlb_overlap_ref_batch() the candidate pairs and their
+ *  ordered seed lists (the reference's String_Olap_t / Match_Node_t lists just
+ *  before Process_Matches) can be read back.  */
+typedef struct {
+  uint32_t ref_id, hash_id;
+  int32_t  dir, consistent, diag_ct, diag_bgn, diag_end, n_seeds;
+  int64_t  seed_begin;
+} ovlb_pair_info;
+typedef struct { int32_t start, offset, len; } ovlb_seed;
+int  ovlb_debug_pairs(ovlb_ctx *ctx, ovlb_pair_info *pairs, uint64_t pair_cap, uint64_t *n_pairs,
+                      ovlb_seed *seeds, uint64_t seed_cap, uint64_t *n_seeds);
+
+/*  Extend one seed between two reads already on the device (ref batch read
+ *  `ref_index` in orientation `dir`, hash read `hash_index`) exactly as
+ *  Extend_Alignment would; out[0..7) = s_lo, s_hi, t_lo, t_hi, errors, kind, delta_ct.
+ *  deltas (optional) receives Left_Delta.  */
+int  ovlb_debug_extend(ovlb_ctx *ctx, uint32_t n, const uint32_t *ref_index, const int32_t *dir,
+                       const uint32_t *hash_index, const int32_t *seed_start, const int32_t *seed_offset,
+                       const int32_t *seed_len, int32_t *out7, int32_t *deltas, uint32_t delta_stride);
+
+/* ---------------------------------------------------------------------------------------------
+ *  Host-side helpers (plain C++, no CUDA): the parts of overlapInCore's main() and of the
+ *  prefixEditDistance constructor that turn command-line values into the tables above.
+ * ------------------------------------------------------------------------------------------- */
+
+/*  Fill *p from command-line level values, computing every derived field and the
+ *  Edit_Match_Limit table exactly as the reference does:
+ *    max_erate / align_noise  must already be rounded through float (the reference parses
+ *                             them with strtof, overlapInCore.C:380-382); ovlb_parse_erate() does it.
+ *    use_hopeless_check       = !no_hopeless && !(max_erate > 0.06)          (overlapInCore.C:400-401)
+ *    filter_by_kmer_count     = min_kmers ? floor(exp(-K*erate)*(minlen-K+1)) : 0   (:410-411)
+ *    MAX_ERRORS, Branch_Match_Value, MIN_BRANCH_TAIL_SLOPE, Edit_Match_Limit
+ *                             (liboverlap/prefixEditDistance.C:23-107, Binomial_Bound.C:104-188)
+ *  The table is heap-allocated; release it with ovlb_params_free().  */
+int    ovlb_params_init(ovlb_params *p, uint32_t kmer_len, double max_erate, double align_noise,
+                        int partial, int unique_per_pair, int min_olap_len, int no_hopeless, int min_kmers,
+                        uint32_t max_read_len);
+void   ovlb_params_free(ovlb_params *p);
+double ovlb_parse_erate(const char *text);        /* (double)strtof(text) */
+
+/*  Pack n ASCII reads (any case; ACGT + N; anything else is an error) into the ovlb_reads wire
+ *  format.  bases/offsets/lens describe the ASCII input.  The returned object owns its buffers;
+ *  release with ovlb_reads_free().  Reads shorter than min_len get len 0 (slot kept).  */
+typedef struct ovlb_reads_owner ovlb_reads_owner;
+int    ovlb_pack_reads(const char *bases, const uint64_t *offsets, const uint32_t *lens, uint32_t n_reads,
+                       uint32_t first_read_id, uint32_t min_len, ovlb_reads_owner **out);
+const ovlb_reads *ovlb_reads_view(const ovlb_reads_owner *o);
+void   ovlb_reads_free(ovlb_reads_owner *o);
+
+/*  k-mer text -> key (base j in bits 2j..2j+1); returns 0 on success, fills fwd and reverse-complement keys. */
+int    ovlb_kmer_keys(const char *kmer, uint32_t kmer_len, uint64_t *fwd_key, uint64_t *rc_key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,194 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(canu_b200/libovlb200.so via canu_b200/api.py); the oracle is only the checker."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    import canu_b200.api as api
+    if api.load_library().ovlb_device_count() == 0:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box")
+    return api
+
+
+def _params(api, kw):
+    return api.OverlapParams(kmer_len=kw.get("kmer_len", 22), max_erate=kw.get("max_erate", 0.06),
+                             partial=kw.get("partial", False), unique=kw.get("unique", True),
+                             min_olap_len=kw.get("min_olap_len", 0), no_hopeless=kw.get("no_hopeless", False),
+                             min_kmers=kw.get("min_kmers", False))
+
+
+def _diff_msg(got, want, limit=6):
+    sg, sw = set(got), set(want)
+    return "only GPU (%d): %s\nonly reference (%d): %s" % (
+        len(sg - sw), sorted(sg - sw)[:limit], len(sw - sg), sorted(sw - sg)[:limit])
+
+
+@pytest.mark.parametrize("case", gu.case_names())
+def test_golden_case_bit_exact(case):
+    """Whole tile vs the reference binary's output: overlaps, -s counters, .oc counts."""
+    api = _api()
+    c = gu.get_case(case)
+    reads = gu.load_dump_reads(c["store"])
+    kw, skip = gu.flags_to_kwargs(c["flags"])
+    recs, ctr = api.overlap_in_core(reads, _params(api, kw), hash_range=tuple(c["h"]), ref_range=tuple(c["r"]),
+                                    skip_kmers=gu.skip_kmers(skip) if skip else None)
+    got, want = gu.format_records(recs), gu.load_golden_lines(case)
+    assert got == want, _diff_msg(got, want)
+    ok, exp = gu.stats_match(gu.load_golden_stats(case), ctr)
+    assert ok, (exp, gu.load_golden_stats(case))
+    n, opr = gu.oc_from_records(recs, len(reads))
+    gn, gopr = gu.load_golden_oc(case)
+    assert n == gn and np.array_equal(opr, gopr)
+
+
+def test_small_ref_batches_give_identical_output():
+    """Output must not depend on how the ref range is batched."""
+    api = _api()
+    c = gu.get_case("A_default")
+    reads = gu.load_dump_reads("A")
+    kw, _ = gu.flags_to_kwargs(c["flags"])
+    r1, c1 = api.overlap_in_core(reads, _params(api, kw))
+    r2, c2 = api.overlap_in_core(reads, _params(api, kw), ref_batch_bases=100000)
+    assert gu.format_records(r1) == gu.format_records(r2)
+    for k in ("kmer_hits_without_olap", "kmer_hits_with_olap", "total_overlaps", "contained", "dovetail"):
+        assert c1[k] == c2[k]
+
+
+@pytest.mark.parametrize("store,erate", [("A", 0.045), ("B", 0.12), ("C", 0.01)])
+def test_seed_lists_match_oracle(store, erate):
+    """K1-K3 at kernel granularity: candidate pairs and their ordered seed lists."""
+    from oracle import oracle_py as op
+    api = _api()
+    reads = gu.load_dump_reads(store)
+    o = op.Oracle(kmer_len=22, max_erate=erate, min_olap_len=500, hash_bits=20, hash_load=0.8, no_hopeless=True)
+    o.set_reads(reads)
+    o.run(threads=8, trace_pairs=True)
+    pt, sd = o.pair_traces()
+    ost = o.stats()
+    o.close()
+    want = {}
+    for p in pt:
+        b, n = int(p["seed_begin"]), int(p["n_seeds"])
+        s = sd[b:b + n]
+        want[(int(p["ref_id"]), int(p["dir"]), int(p["hash_id"]))] = (
+            int(p["consistent"]), int(p["diag_ct"]), int(p["diag_bgn"]), int(p["diag_end"]),
+            list(zip(s["start"].tolist(), s["offset"].tolist(), s["len"].tolist())))
+
+    prm = api.OverlapParams(kmer_len=22, max_erate=erate, min_olap_len=500, no_hopeless=True,
+                            max_read_len=max(len(r) for r in reads))
+    ov = api.Overlapper(prm)
+    pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+    ov.load_hash_reads(pk)
+    ov.build_index()
+    ov.stage_ref_batch(pk)
+    ov.run_staged()
+    pairs, seeds = ov.debug_pairs()
+    got = {}
+    for p in pairs:
+        b, n = int(p["seed_begin"]), int(p["n_seeds"])
+        s = seeds[b:b + n]
+        got[(int(p["ref_id"]), int(p["dir"]), int(p["hash_id"]))] = (
+            int(p["consistent"]) & 1, int(p["diag_ct"]), int(p["diag_bgn"]), int(p["diag_end"]),
+            list(zip(s["start"].tolist(), s["offset"].tolist(), s["len"].tolist())))
+    ctr = ov.counters()
+    ov.close()
+    assert set(got) == set(want), (len(got), len(want), sorted(set(got) ^ set(want))[:5])
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, (len(bad), bad[:3], [(got[k], want[k]) for k in bad[:1]])
+    assert ctr["seed_hits"] == ost["seed_hits"]
+    assert ctr["hash_kmers"] == ost["hash_inserts"]
+    assert ctr["ref_kmers"] == ost["ref_lookups"]
+
+
+@pytest.mark.parametrize("store,erate,partial", [("A", 0.045, False), ("B", 0.06, False), ("B", 0.15, True), ("C", 0.01, False)])
+def test_extension_kernel_matches_oracle_calls(store, erate, partial):
+    """K4 at kernel granularity: every Extend_Alignment call the oracle made, re-run on the GPU from
+    the same seed: (S_Lo,S_Hi,T_Lo,T_Hi,Errors,kind,delta_ct) must be identical, and the DP cell count too."""
+    from oracle import oracle_py as op
+    api = _api()
+    reads = gu.load_dump_reads(store)
+    o = op.Oracle(kmer_len=22, max_erate=erate, min_olap_len=500, hash_bits=20, hash_load=0.8, partial=partial)
+    o.set_reads(reads)
+    o.run(threads=8, trace_exts=True)
+    et = o.ext_traces()
+    ost = o.stats()
+    o.close()
+    assert len(et) > 100
+
+    prm = api.OverlapParams(kmer_len=22, max_erate=erate, min_olap_len=500, partial=partial,
+                            max_read_len=max(len(r) for r in reads))
+    ov = api.Overlapper(prm)
+    pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+    ov.load_hash_reads(pk)
+    ov.build_index()
+    ov.stage_ref_batch(pk)
+    ov.reset_counters()
+    out, _ = ov.debug_extend(et["ref_id"] - 1, et["dir"], et["hash_id"] - 1, et["seed_start"], et["seed_offset"], et["seed_len"])
+    ctr = ov.counters()
+    ov.close()
+    want = np.stack([et[f] for f in ("s_lo", "s_hi", "t_lo", "t_hi", "errors", "kind", "delta_ct")], axis=1)
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, (bad.size, len(et), [(et[i].tolist(), out[i].tolist()) for i in bad[:4]])
+    assert ctr["dp_cells"] == ost["dp_cells"], (ctr["dp_cells"], ost["dp_cells"])
+    assert ctr["extend_calls"] == ost["extend_calls"]
+
+
+def test_delta_encoding_matches_oracle():
+    """Left_Delta itself (only delta_ct reaches the output, but Lies_On_Alignment walks the values)."""
+    from oracle import oracle_py as op
+    api = _api()
+    reads = gu.load_dump_reads("B")
+    o = op.Oracle(kmer_len=22, max_erate=0.12, min_olap_len=500, hash_bits=20, hash_load=0.8)
+    o.set_reads(reads)
+    o.run(threads=8, trace_exts=True)
+    et = o.ext_traces()
+    sel = et[np.argsort(-et["delta_ct"], kind="stable")[:300]]
+    prm = api.OverlapParams(kmer_len=22, max_erate=0.12, min_olap_len=500, max_read_len=max(len(r) for r in reads))
+    ov = api.Overlapper(prm)
+    pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+    ov.load_hash_reads(pk)
+    ov.build_index()
+    ov.stage_ref_batch(pk)
+    stride = int(sel["delta_ct"].max()) + 4
+    out, deltas = ov.debug_extend(sel["ref_id"] - 1, sel["dir"], sel["hash_id"] - 1, sel["seed_start"], sel["seed_offset"],
+                                  sel["seed_len"], delta_stride=stride)
+    ov.close()
+    lower = [bytes(r).lower() for r in reads]
+    comp = bytes.maketrans(b"acgtn", b"tgcan")
+    for i, t in enumerate(sel):
+        S = lower[t["ref_id"] - 1]
+        if t["dir"]:
+            S = S.translate(comp)[::-1]
+        T = lower[t["hash_id"] - 1]
+        res, d = o.extend_one(S, T, int(t["seed_start"]), int(t["seed_offset"]), int(t["seed_len"]))
+        assert int(res["delta_ct"]) == int(out[i, 6]) == int(t["delta_ct"])
+        assert np.array_equal(d, deltas[i, : len(d)]), (i, d[:10], deltas[i, :10])
+    o.close()
+
+
+def test_empty_and_degenerate_inputs():
+    api = _api()
+    prm = api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500)
+    # no reads at all
+    recs, ctr = api.overlap_in_core([], prm)
+    assert len(recs) == 0 and ctr["total_overlaps"] == 0
+    # reads all shorter than --minlength: nothing hashed, nothing searched
+    short = [np.frombuffer(b"ACGT" * 50, dtype=np.uint8)] * 4
+    recs, ctr = api.overlap_in_core(short, prm)
+    assert len(recs) == 0
+    # two identical reads: one contained overlap with zero hangs, zero error
+    import canu_b200.synth as synth
+    g = synth.make_genome(3000, 5)
+    recs, ctr = api.overlap_in_core([g, g.copy()], prm)
+    assert len(recs) == 1 and ctr["contained"] == 1
+    f = recs[0]
+    assert (f["a_iid"], f["b_iid"]) == (1, 2) and (f["w0"] & ((1 << 58) - 1)) == 0
+    # an all-N read is stored but can never seed
+    n_read = np.full(2000, ord("N"), dtype=np.uint8)
+    recs, ctr = api.overlap_in_core([g, n_read, g.copy()], prm)
+    assert len(recs) == 1 and (recs[0]["a_iid"], recs[0]["b_iid"]) == (1, 3)
