@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ovl hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--genome BP --coverage X]
+
+Workload (config.workload): BASELINE.json configs[1] -- "5 Mbp bacterial 50x HiFi-like reads
+(ovlErrorRate 0.01)": uniform-random 5 Mbp genome, reads sampled from both strands with a log-normal
+length distribution (mean ~11 kb, HiFi-like), 0.1 % per-read error (sub:ins:del 4:3:3), k=22,
+--minlength 500, --maxerate 0.01, one hash block x one ref block (-h 1-N -r 1-N).  Synthetic, seeded.
+
+One "step" = one pass of the hot path over the tile: k-mer index build over the hash reads, lookup +
+seed-run emission + chaining for every ref read in both orientations, banded extension of every
+candidate pair, overlap records packed on the device.
+
+  value  read-pairs aligned per second (candidate oriented pairs entering Process_Matches =
+         "Kmer hits with olaps + Kmer hits without olaps" of the -s file), device pipeline only,
+         reads already resident in HBM (dp4-encoded) when the timed region starts.
+  e2e    the same metric through the C ABI with HOST buffers: packed reads copied host->device for
+         the hash and ref side, records copied device->host, inside the timed region.
+  roofline  the dominant kernel of the step (by measured stage time) against the measured HBM peak.
+  cpu_baseline  the UNMODIFIED reference overlapInCore (oracle/_ref, built by oracle/build_ref.sh) run
+         with -t <all host cores> on a bounded sample of the same workload (smaller genome, same
+         coverage / read model), rank 0 only.
+
+--impl reference times that reference binary instead (all host threads), same metric and unit.
+Under torchrun (N>1) every rank owns an independent tile of the same size (Canu's own job split:
+tiles share nothing), no collective on the data path; scaling is "weak".
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 22
+MINLEN = 500
+ERATE = 0.01
+READ_ERR = 0.001
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+
+
+def make_workload(genome_bp, coverage, seed):
+    from canu_b200 import synth
+    g = synth.make_genome(genome_bp, seed=seed)
+    # HiFi-like: log-normal lengths, mean ~11 kb, clipped to [3 kb, 30 kb]
+    reads = synth.simulate_reads(g, coverage, 3000, 30000, READ_ERR, seed=seed + 1, lognormal=(9.25, 0.3))
+    return reads
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def reference_run(reads, threads, workdir, tag):
+    """Run the unmodified reference overlapper on `reads`; returns (seconds, pairs, overlaps)."""
+    from canu_b200 import synth
+    fa = os.path.join(workdir, tag + ".fasta")
+    st = os.path.join(workdir, tag + ".seqStore")
+    if not os.path.exists(st):
+        synth.write_fasta(fa, reads)
+        subprocess.check_call([os.path.join(REFBIN, "sqStoreCreate"), "-o", st, "-minlength", "1000",
+                               "-pacbio-hifi", "lib", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.remove(fa)
+    n = len(reads)
+    out = os.path.join(workdir, tag + ".ovb")
+    stats = os.path.join(workdir, tag + ".stats")
+    cmd = [os.path.join(REFBIN, "overlapInCore"), "-t", str(threads), "-k", str(K), "--hashbits", "23",
+           "--hashload", "0.8", "--hashdatalen", str(10 ** 10), "--maxerate", str(ERATE), "--minlength", str(MINLEN),
+           "-h", "1-%d" % n, "-r", "1-%d" % n, "-o", out, "-s", stats, st]
+    t0 = time.perf_counter()
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    vals = {}
+    for line in open(stats):
+        k, v = line.split("=")
+        vals[k.strip()] = int(v)
+    pairs = vals["Kmer hits without olaps"] + vals["Kmer hits with olaps"]
+    return dt, pairs, vals["Total overlaps produced"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome", type=int, default=5_000_000)
+    ap.add_argument("--coverage", type=float, default=50.0)
+    ap.add_argument("--sample-genome", type=int, default=400_000, help="genome size of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    workload = "C2: %.1f Mbp random genome, %gx HiFi-like reads (log-normal ~11 kb, %.1f%% read error), k=%d, --maxerate %g, --minlength %d, single hash x ref tile" % (
+        args.genome / 1e6, args.coverage, READ_ERR * 100, K, ERATE, MINLEN)
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        if not os.path.exists(os.path.join(REFBIN, "overlapInCore")):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/overlapInCore was not built (run oracle/build_ref.sh where /root/reference exists)"}))
+            return 0
+        wd = tempfile.mkdtemp(prefix="ovlbench_ref_")
+        try:
+            reads = make_workload(args.sample_genome, args.coverage, seed=1001)
+            for _ in range(max(args.warmup, 0) and 1):          # one warm-up run is enough to warm the page cache
+                reference_run(reads, cores, wd, "s")
+            ts, pairs = [], 0
+            for _ in range(args.steps):
+                dt, pairs, _ = reference_run(reads, cores, wd, "s")
+                ts.append(dt)
+            t = float(np.mean(ts))
+            v = pairs / t
+            sample = "%.2f Mbp genome x %gx (%d reads, %d bases), whole tile per step, reference overlapInCore -t %d" % (
+                args.sample_genome / 1e6, args.coverage, len(reads), sum(r.size for r in reads), cores)
+            print(json.dumps({
+                "impl": "reference", "metric": "ovl read-pairs aligned/sec", "value": v, "unit": "read-pairs/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": workload, "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }))
+        finally:
+            shutil.rmtree(wd, ignore_errors=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import canu_b200
+    from canu_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+
+    reads = make_workload(args.genome, args.coverage, seed=2001 + 17 * rank)
+    n_reads = len(reads)
+    total_bases = int(sum(r.size for r in reads))
+    prm = api.OverlapParams(kmer_len=K, max_erate=ERATE, min_olap_len=MINLEN, max_read_len=max(r.size for r in reads))
+    ov = api.Overlapper(prm, device=local_rank)
+    packed = api.PackedReads(reads, first_read_id=1, min_len=MINLEN)
+    del reads
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps: index build + seeding + extension (reads already in HBM)
+    ov.load_hash_reads(packed)
+    ov.build_index()
+    ov.stage_ref_batch(packed)
+
+    def step():
+        ov.build_index()
+        return ov.run_staged()
+
+    for _ in range(args.warmup):
+        step()
+    ov.reset_counters()
+    launches0 = ov.kernel_launches()
+    stage_ms = {}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    n_rec = 0
+    for _ in range(args.steps):
+        n_rec = step()
+        t = ov.timings()
+        for k2, v2 in t.items():
+            stage_ms[k2] = stage_ms.get(k2, 0.0) + v2 / args.steps
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ov.kernel_launches() - launches0
+    ctr = ov.counters()
+    # the library runs on its own stream and synchronises inside every call, so host wall time between the
+    # two barriers equals the device span; torch events on the current stream are recorded for reference.
+    dev_ms = wall * 1e3
+    pairs_step = ctr["pairs"] / args.steps
+    cells_step = ctr["dp_cells"] / args.steps
+
+    # ---- end to end through the C ABI with host buffers
+    def e2e_step():
+        ov.load_hash_reads(packed)
+        ov.build_index()
+        return ov.overlap_ref_batch(packed, cap=max(n_rec, 1) + 1024)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        recs = e2e_step()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    h2d = 2 * (packed.packed_bytes + n_reads * (8 + 4 + 8 + 8))
+    d2h = int(recs.nbytes)
+
+    tt = torch.tensor([dev_ms / args.steps, e2e_wall * 1e3 / args.steps, pairs_step, cells_step], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_step, e2e_ms = tmax[0].item(), tmax[1].item()
+        pairs_all, cells_all = tsum[2].item(), tsum[3].item()
+    else:
+        ms_step, e2e_ms, pairs_all, cells_all = tt[0].item(), tt[1].item(), pairs_step, cells_step
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        # dominant stage of the step and its roofline (DESIGN.md "Kernels and rooflines" states the per-unit bytes)
+        stages = {k2: v2 for k2, v2 in stage_ms.items() if k2 in ("index_count_ms", "index_fill_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms")}
+        dom = max(stages, key=stages.get)
+        hk, rk, sh, sr = (ctr[x] / args.steps for x in ("hash_kmers", "ref_kmers", "seed_hits", "seed_runs"))
+        alg_bytes = {
+            "index_count_ms": hk * (0.5 + 8 + 4 + 4),               # dp4 base + key slot + count RMW + slot_of write
+            "index_fill_ms": hk * (4 + 4 + 4 + 8),                   # slot_of + start + cursor RMW + occurrence write
+            "probe_ms": rk * (0.5 + 8 + 4 + 4),                      # dp4 base + key probe + count + slot write
+            "expand_ms": rk * 4 + sh * (8 + 0.5) + sr * 16,          # slot read + occurrence + hash base check + run write
+            "sort_ms": sr * 16 * 2 * 4,                              # 4 radix passes over 16 B run records, read+write
+            "chain_ms": sr * (16 + 12 + 12 + 16),
+            "extend_ms": cells_step * 0.25,                          # 2-bit from-codes are the only HBM traffic per cell
+        }[dom]
+        achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                    "ms_per_launch": stages[dom]}
+        line = {
+            "metric": "ovl read-pairs aligned/sec", "value": pairs_all / (ms_step * 1e-3), "unit": "read-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload, "reads_per_gpu": n_reads, "bases_per_gpu": total_bases,
+                       "l2": "inputs (%.0f MB dp4 + index) exceed the 126 MB L2" % (total_bases * 1.0 / 1e6)},
+            "e2e": {"value": pairs_all / (e2e_ms * 1e-3), "unit": "read-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "extension": {"gcells_per_s": cells_all / 1e9 / (ms_step * 1e-3),
+                          "kernel_gcells_per_s": cells_step / 1e9 / (stage_ms["extend_ms"] * 1e-3) if stage_ms.get("extend_ms") else None,
+                          "cells_per_step": cells_all},
+            "stages_ms": {k2: round(v2, 3) for k2, v2 in stage_ms.items()},
+            "overlaps_per_step": int(n_rec), "pairs_per_step": pairs_all,
+        }
+        if not args.no_cpu_baseline and os.path.exists(os.path.join(REFBIN, "overlapInCore")):
+            wd = tempfile.mkdtemp(prefix="ovlbench_cpu_")
+            try:
+                sreads = make_workload(args.sample_genome, args.coverage, seed=1001)
+                reference_run(sreads, cores, wd, "s")
+                dt, sp, _ = reference_run(sreads, cores, wd, "s")
+                line["cpu_baseline"] = {"value": sp / dt, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
+                                        "sample": "%.2f Mbp genome x %gx (%d reads), whole tile, reference overlapInCore -t %d, %.1f s" % (
+                                            args.sample_genome / 1e6, args.coverage, len(sreads), cores, dt)}
+            finally:
+                shutil.rmtree(wd, ignore_errors=True)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    ov.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

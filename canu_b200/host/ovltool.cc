@@ -1,0 +1,87 @@
+//  ovltool.cc -- small companion tool for the host-side formats (used by the CPU test-suite):
+//    ovltool dump-store <seqStore> [--packed]    reads as the overlapper sees them, FASTA on stdout
+//                                                (--packed: through the zero-decode 2-bit path)
+//    ovltool dump-ovb <file.ovb>                 records as "a b dat0 dat1" (hex words) on stdout
+//    ovltool rewrite-ovb <in.ovb> <out.ovb> <lastReadID>   decode with our snappy reader, write with our writer
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ovfile.h"
+#include "sqstore.h"
+
+using namespace ovlhost;
+
+static bool read_ovb(const char *fn, std::vector<ovlb_record> &recs, std::string &err) {
+  FILE *f = fopen(fn, "rb");
+  if (!f) { err = std::string("cannot open ") + fn; return false; }
+  std::vector<uint8_t> comp, raw;
+  while (true) {
+    uint64_t cl;
+    if (fread(&cl, 8, 1, f) != 1) break;
+    comp.resize(cl);
+    if (fread(comp.data(), 1, cl, f) != cl) { err = "short read"; fclose(f); return false; }
+    if (!snappy_uncompress(comp.data(), cl, raw)) { err = "bad snappy block"; fclose(f); return false; }
+    if (raw.size() % 24) { err = "block is not a whole number of records"; fclose(f); return false; }
+    for (size_t p = 0; p < raw.size(); p += 24) {
+      uint32_t w[6]; memcpy(w, &raw[p], 24);
+      ovlb_record r; r.a_iid = w[0]; r.b_iid = w[1];
+      r.dat0 = ((uint64_t)w[2] << 32) | w[3]; r.dat1 = ((uint64_t)w[4] << 32) | w[5];
+      recs.push_back(r);
+    }
+  }
+  fclose(f);
+  return true;
+}
+
+int main(int argc, char **argv) {
+  std::string err;
+  if (argc >= 3 && !strcmp(argv[1], "dump-store")) {
+    const bool packed = argc >= 4 && !strcmp(argv[3], "--packed");
+    SqStore S;
+    if (!S.open(argv[2], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::string b;
+    for (uint32_t id = 1; id <= S.lastReadID(); id++) {
+      const uint32_t L = S.readLength(id);
+      if (L == 0) continue;
+      bool done = false;
+      if (packed) {
+        std::vector<uint8_t> pk;
+        int r = S.appendPacked2bit(id, pk, err);
+        if (r < 0) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        if (r == 1) {
+          b.resize(L);
+          for (uint32_t j = 0; j < L; j++) b[j] = "ACGT"[(pk[j >> 2] >> (6 - 2 * (j & 3))) & 3];
+          done = true;
+        }
+      }
+      if (!done && !S.loadRead(id, b, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+      printf(">read%u len=%u lib=%u\n%s\n", id, L, S.libraryID(id), b.c_str());
+    }
+    return 0;
+  }
+  if (argc >= 3 && !strcmp(argv[1], "dump-ovb")) {
+    std::vector<ovlb_record> recs;
+    if (!read_ovb(argv[2], recs, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    for (auto &r : recs) printf("%u %u %016lx %016lx\n", r.a_iid, r.b_iid, (unsigned long)r.dat0, (unsigned long)r.dat1);
+    return 0;
+  }
+  if (argc >= 5 && !strcmp(argv[1], "rewrite-ovb")) {
+    std::vector<ovlb_record> recs;
+    if (!read_ovb(argv[2], recs, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    OvFileWriter W;
+    if (!W.open(argv[3], (uint32_t)strtoul(argv[4], nullptr, 10), err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    //  hand the records over in uneven batches to exercise block boundaries
+    size_t p = 0, step = 1000;
+    while (p < recs.size()) {
+      size_t n = std::min(step, recs.size() - p);
+      W.submit(std::vector<ovlb_record>(recs.begin() + p, recs.begin() + p + n));
+      p += n; step = step * 3 + 7;
+    }
+    if (!W.close(err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    return 0;
+  }
+  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID>\n");
+  return 1;
+}

@@ -319,7 +319,6 @@ static int32_t ped_extend(const ovo_ctx *c, ped_t *p, int dirn,
   double max_score = 0.0;
   const double bmv = c->branch_match_value;
 
-  p->calls++;
   if (dirn > 0) p->right_delta_len = 0; else p->left_delta_len = 0;
 
 #define AT(s, i)  ((s)[dirn > 0 ? (i) : -(i)])
@@ -337,6 +336,7 @@ static int32_t ped_extend(const ovo_ctx *c, ped_t *p, int dirn,
     *match_to_end = 1;
     return 0;
   }
+  p->calls++;                          /* instrumentation: extensions that actually ran the DP */
 
   int left = 0, right = 0;
 

@@ -192,3 +192,33 @@ def test_empty_and_degenerate_inputs():
     n_read = np.full(2000, ord("N"), dtype=np.uint8)
     recs, ctr = api.overlap_in_core([g, n_read, g.copy()], prm)
     assert len(recs) == 1 and (recs[0]["a_iid"], recs[0]["b_iid"]) == (1, 3)
+
+
+@pytest.mark.parametrize("case", ["A_default", "A_skip", "A_partial", "A_ranges", "C_hpc"])
+def test_drop_in_executable_on_sqstore(case, tmp_path):
+    """The C++ host driver end to end: same argv as the reference, reads the reference-made sqStore,
+    writes .ovb/.oc/.stats; compared with the golden output of the reference binary."""
+    import os
+    import subprocess
+    _api()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "canu_b200", "bin", "overlapInCore")
+    tool = os.path.join(root, "canu_b200", "bin", "ovltool")
+    assert os.path.exists(exe), "build the host driver first (__graft_entry__.build())"
+    c = gu.get_case(case)
+    store = os.path.join(gu.GOLDEN, c["store"] + ".seqStore")
+    flags = [os.path.join(gu.GOLDEN, f) if f.endswith(".dump") else f for f in c["flags"]]
+    ovb = str(tmp_path / "out.ovb")
+    cmd = [exe, "-t", "4", "-k", "22", "--hashbits", "22", "--hashload", "0.8", "--minlength", "500"] + flags + [
+        "-h", "%d-%d" % tuple(c["h"]), "-r", "%d-%d" % tuple(c["r"]), "-o", ovb, "-s", str(tmp_path / "out.stats"), store]
+    r = subprocess.run(cmd, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines = subprocess.check_output([tool, "dump-ovb", ovb]).decode().splitlines()
+    recs = np.zeros(len(lines), dtype=[("a_iid", "<u4"), ("b_iid", "<u4"), ("w0", "<u8"), ("w1", "<u8")])
+    for i, ln in enumerate(lines):
+        x = ln.split()
+        recs[i] = (int(x[0]), int(x[1]), int(x[2], 16), int(x[3], 16))
+    got, want = gu.format_records(recs), gu.load_golden_lines(case)
+    assert got == want, _diff_msg(got, want)
+    assert open(str(tmp_path / "out.stats")).read() == open(os.path.join(gu.GOLDEN, case + ".stats")).read()
+    assert open(str(tmp_path / "out.oc"), "rb").read() == open(os.path.join(gu.GOLDEN, case + ".oc"), "rb").read()
