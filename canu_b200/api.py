@@ -71,7 +71,7 @@ EXPORTS = [
     "ovlb_last_error", "ovlb_device_count", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
-    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_debug_pairs", "ovlb_debug_extend",
+    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_debug_pairs", "ovlb_debug_extend",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
     "ovlb_reads_free", "ovlb_kmer_keys",
 ]
@@ -102,6 +102,8 @@ def load_library():
     L.ovlb_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
     L.ovlb_kernel_launches.argtypes = [C.c_void_p]
     L.ovlb_kernel_launches.restype = C.c_uint64
+    L.ovlb_timer_start.argtypes = [C.c_void_p]
+    L.ovlb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.ovlb_debug_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
@@ -279,6 +281,14 @@ class Overlapper:
 
     def kernel_launches(self) -> int:
         return self.L.ovlb_kernel_launches(self._h)
+
+    def timer_start(self):
+        _check(self.L.ovlb_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(self.L.ovlb_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     # --- debug taps (tests) ---
     def debug_pairs(self):

@@ -60,12 +60,13 @@ int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   c->mem_budget = p->device_mem_budget ? p->device_mem_budget : (uint64_t)(free_b * 0.8);
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaMalloc((void **)&c->d_eml, (size_t)p->n_edit_match_limit * 4));
-  CK(cudaMemcpy(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpyAsync(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice, c->stream));
   c->P.edit_match_limit = nullptr;                     // caller's buffer is not retained
   CK(cudaMalloc((void **)&c->d_counters, sizeof(DevCounters)));
-  CK(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  CK(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
   CK(cudaMalloc((void **)&c->d_work, 64));
-  CK(cudaMemset(c->d_work, 0, 64));
+  CK(cudaMemsetAsync(c->d_work, 0, 64, c->stream));
+  CK(cudaStreamSynchronize(c->stream));                 // all setup is ordered on the context's own (non-blocking) stream
   c->dp.K = (int)p->kmer_len;
   c->dp.partial = p->partial; c->dp.unique = p->unique_per_pair; c->dp.min_olap_len = p->min_olap_len;
   c->dp.use_hopeless = p->use_hopeless_check;
@@ -95,6 +96,7 @@ void ovlb_destroy(ovlb_ctx *c) {
                    c->run_key, c->run_val, c->run_key2, c->run_val2, c->runs_extra, c->pair_flag, c->pair_idx, c->cub_temp, c->pairs,
                    c->seed_start, c->seed_off, c->seed_len, c->sim_nxt, c->sim_hits, c->sim_act, c->sim_order, c->seed_alive, c->d_records };
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (c->ev_start) { cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); }
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -155,7 +157,7 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
   c->timings.total_ms = tt.stop();
   if (e != cudaSuccess) { ovl_set_error(std::string("extension kernel failed: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; }
   if (flags) {
-    cudaMemset(&c->d_counters->v[CT_ERR_FLAGS], 0, 8);
+    cudaMemsetAsync(&c->d_counters->v[CT_ERR_FLAGS], 0, 8, c->stream);
     ovl_set_error("device buffer overflow in the extension kernel (flags " + std::to_string(flags) + ")");
     return OVLB_ERR_CAPACITY;
   }
@@ -205,7 +207,8 @@ int ovlb_reset_counters(ovlb_ctx *c) {
   if (!c) { ovl_set_error("ovlb_reset_counters: null context"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+  CK(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return OVLB_OK;
 }
 
@@ -216,6 +219,24 @@ int ovlb_get_timings(ovlb_ctx *c, ovlb_timings *out) {
 }
 
 uint64_t ovlb_kernel_launches(ovlb_ctx *c) { return c ? c->launches : 0; }
+
+int ovlb_timer_start(ovlb_ctx *c) {
+  if (!c) { ovl_set_error("ovlb_timer_start: null context"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (!c->ev_start) { CK(cudaEventCreate(&c->ev_start)); CK(cudaEventCreate(&c->ev_stop)); }
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaEventRecord(c->ev_start, c->stream));
+  return OVLB_OK;
+}
+
+int ovlb_timer_stop(ovlb_ctx *c, float *ms) {
+  if (!c || !ms || !c->ev_start) { ovl_set_error("ovlb_timer_stop: no timer running"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev_stop, c->stream));
+  CK(cudaEventSynchronize(c->ev_stop));
+  CK(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+  return OVLB_OK;
+}
 
 int ovlb_debug_pairs(ovlb_ctx *c, ovlb_pair_info *pairs, uint64_t pair_cap, uint64_t *n_pairs,
                      ovlb_seed *seeds, uint64_t seed_cap, uint64_t *n_seeds) {

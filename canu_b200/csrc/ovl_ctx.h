@@ -124,6 +124,7 @@ struct ovlb_ctx {
   unsigned long long *d_work = nullptr;   // persistent-kernel work counters
 
   ovlb_timings timings;
+  cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;     // ovlb_timer_start / ovlb_timer_stop
   uint64_t     launches = 0;
   bool         staged = false;
 };

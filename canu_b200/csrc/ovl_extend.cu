@@ -68,7 +68,7 @@ __device__ __forceinline__ int push_at(const WarpMem &M, int i, int v_start) {
 //  Traceback through the from-codes, then delta encoding.  Returns delta_len; writes deltas to `out`.
 //  fwd_rules: Set_Right_Delta conventions; else Set_Left_Delta (sets leftover, may bump t_mag).
 __device__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
-                              int e_start, int d_start, int v_start, int row0, bool fwd_rules,
+                              int e_start, int d_start, int v_start, int row0, bool fwd_rules, int first_code,
                               int32_t *out, int &leftover, int &t_mag, int lane) {
   //  Phase A: walk down, 32 rows per round
   int n_ind = 0;
@@ -97,6 +97,7 @@ __device__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, cons
       //  note: gi computed from the broadcast (uniform) values, so every lane selects the same word index
       int bit = idx & 31;
       int code = ((x >> bit) & 1) | (((y >> bit) & 1) << 1);
+      if (first_code >= 0 && kb == e_start && l == 0) code = first_code;   // cell the DP never evaluated (forced mismatch)
       if (lane == l) mycode = code;
       if (code == 1) dcur--; else if (code == 2) dcur++;
     }
@@ -261,14 +262,24 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
       }
       if (abort_) {
         o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
-        o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules,
+        o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules, -1,
                                      delta_out, o.leftover, o.t_end, lane);
         return;
       }
       int d = term_d;
-      if (fwd_rules && term_row == m && d < Ru && 1 + prev[(d + 1) & mask] == term_row) d++;   // force last error to be a mismatch
+      int first_code = -1;
+      if (fwd_rules && term_row == m && d < Ru && 1 + prev[(d + 1) & mask] == term_row) {
+        //  Force the last error to be a mismatch (forward.C:215-221): the path now starts in cell (e, d+1), which
+        //  the DP never evaluated (it may lie in a 32-cell group after the one that terminated), so its from-code
+        //  is derived here from row e-1 exactly as Set_Right_Delta does (forward.C:45-55).
+        d++;
+        const int pa = prev[(d - 1) & mask], pb = prev[d & mask], pc = prev[(d + 1) & mask];
+        int mx = 1 + pb; first_code = 0;
+        if (pa > mx) { mx = pa; first_code = 1; }
+        if (1 + pc > mx) first_code = 2;
+      }
       o.a_end = term_row; o.t_end = term_row + d; o.match_to_end = 1; o.errors = e;
-      o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, e, d, term_row, row0, fwd_rules, delta_out, o.leftover, o.t_end, lane);
+      o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, e, d, term_row, row0, fwd_rules, first_code, delta_out, o.leftover, o.t_end, lane);
       return;
     }
     cells += (unsigned long long)width;
@@ -304,7 +315,7 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
 
   //  error limit exhausted or band closed
   o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
-  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules,
+  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules, -1,
                                delta_out, o.leftover, o.t_end, lane);
 }
 
@@ -746,13 +757,13 @@ int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const i
   CK(cudaMalloc((void **)&d_u, (size_t)n * 2 * 4));
   CK(cudaMalloc((void **)&d_i, (size_t)n * 4 * 4));
   CK(cudaMalloc((void **)&d_out, (size_t)n * 7 * 4));
-  if (deltas) { CK(cudaMalloc((void **)&d_del, (size_t)n * delta_stride * 4)); CK(cudaMemset(d_del, 0, (size_t)n * delta_stride * 4)); }
-  CK(cudaMemcpy(d_u, ref_index, (size_t)n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_u + n, hash_index, (size_t)n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_i, dir, (size_t)n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_i + n, seed_start, (size_t)n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_i + 2 * n, seed_offset, (size_t)n * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_i + 3 * n, seed_len, (size_t)n * 4, cudaMemcpyHostToDevice));
+  if (deltas) { CK(cudaMalloc((void **)&d_del, (size_t)n * delta_stride * 4)); CK(cudaMemsetAsync(d_del, 0, (size_t)n * delta_stride * 4, c->stream)); }
+  CK(cudaMemcpyAsync(d_u, ref_index, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_u + n, hash_index, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_i, dir, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_i + n, seed_start, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_i + 2 * n, seed_offset, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_i + 3 * n, seed_len, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->d_work, 0, 64, c->stream));
   const int smem = EXT_WARPS * 2 * SRING * 4;
   int blocks = c->ext.n_warps / EXT_WARPS;
@@ -765,8 +776,9 @@ int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const i
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
-  CK(cudaMemcpy(out7, d_out, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost));
-  if (deltas) CK(cudaMemcpy(deltas, d_del, (size_t)n * delta_stride * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(out7, d_out, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (deltas) CK(cudaMemcpyAsync(deltas, d_del, (size_t)n * delta_stride * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   cudaFree(d_u); cudaFree(d_i); cudaFree(d_out); if (d_del) cudaFree(d_del);
   return OVLB_OK;
 }

@@ -165,6 +165,12 @@ int  ovlb_reset_counters(ovlb_ctx *ctx);
 int  ovlb_get_timings(ovlb_ctx *ctx, ovlb_timings *out);
 uint64_t ovlb_kernel_launches(ovlb_ctx *ctx);   /* kernels launched by this context so far */
 
+/*  Device-time bracket for benchmarks: CUDA events recorded on the context's own stream (the stream
+ *  every kernel of this context is launched on).  ovlb_timer_stop() synchronises and returns the
+ *  elapsed milliseconds between the two events.  */
+int  ovlb_timer_start(ovlb_ctx *ctx);
+int  ovlb_timer_stop(ovlb_ctx *ctx, float *ms);
+
 /*  Kernel-granularity debug taps used by the parity tests (tests/ only).  After
  *  ovlb_run_staged()/ovlb_overlap_ref_batch() the candidate pairs and their
  *  ordered seed lists (the reference's String_Olap_t / Match_Node_t lists just

@@ -133,7 +133,8 @@ def test_extension_kernel_matches_oracle_calls(store, erate, partial):
     ov.close()
     want = np.stack([et[f] for f in ("s_lo", "s_hi", "t_lo", "t_hi", "errors", "kind", "delta_ct")], axis=1)
     bad = np.nonzero((out != want).any(axis=1))[0]
-    assert bad.size == 0, (bad.size, len(et), [(et[i].tolist(), out[i].tolist()) for i in bad[:4]])
+    assert bad.size == 0, "%d of %d extensions differ:\n%s" % (bad.size, len(et), "\n".join(
+        "in %s\n  want %s\n  got  %s" % (et[i].tolist()[:6], want[i].tolist(), out[i].tolist()) for i in bad[:6]))
     assert ctr["dp_cells"] == ost["dp_cells"], (ctr["dp_cells"], ost["dp_cells"])
     assert ctr["extend_calls"] == ost["extend_calls"]
 
@@ -187,11 +188,12 @@ def test_empty_and_degenerate_inputs():
     recs, ctr = api.overlap_in_core([g, g.copy()], prm)
     assert len(recs) == 1 and ctr["contained"] == 1
     f = recs[0]
-    assert (f["a_iid"], f["b_iid"]) == (1, 2) and (f["w0"] & ((1 << 58) - 1)) == 0
+    # equal hangs: Output_Overlap picks the hash read as A (Output.C:60-75); the oracle agrees: (2, 1)
+    assert (f["a_iid"], f["b_iid"]) == (2, 1) and (f["w0"] & ((1 << 58) - 1)) == 0
     # an all-N read is stored but can never seed
     n_read = np.full(2000, ord("N"), dtype=np.uint8)
     recs, ctr = api.overlap_in_core([g, n_read, g.copy()], prm)
-    assert len(recs) == 1 and (recs[0]["a_iid"], recs[0]["b_iid"]) == (1, 3)
+    assert len(recs) == 1 and (recs[0]["a_iid"], recs[0]["b_iid"]) == (3, 1)
 
 
 @pytest.mark.parametrize("case", ["A_default", "A_skip", "A_partial", "A_ranges", "C_hpc"])
