@@ -275,15 +275,17 @@ def main():
     if rank == 0:
         peaks, which = measured_peaks()
         # dominant stage of the step and its roofline (DESIGN.md "Kernels and rooflines" states the per-unit bytes)
-        stages = {k2: v2 for k2, v2 in stage_ms.items() if k2 in ("index_count_ms", "index_fill_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms")}
+        stages = {k2: v2 for k2, v2 in stage_ms.items() if k2 in ("index_tuples_ms", "index_sort_ms", "index_table_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms")}
         dom = max(stages, key=stages.get)
         hk, rk, sh, sr = (ctr[x] / args.steps for x in ("hash_kmers", "ref_kmers", "seed_hits", "seed_runs"))
+        # algorithmic bytes per unit: DESIGN.md section 4
         alg_bytes = {
-            "index_count_ms": hk * (0.5 + 8 + 4 + 4),               # dp4 base + key slot + count RMW + slot_of write
-            "index_fill_ms": hk * (4 + 4 + 4 + 8),                   # slot_of + start + cursor RMW + occurrence write
-            "probe_ms": rk * (0.5 + 8 + 4 + 4),                      # dp4 base + key probe + count + slot write
-            "expand_ms": rk * 4 + sh * (8 + 0.5) + sr * 16,          # slot read + occurrence + hash base check + run write
-            "sort_ms": sr * 16 * 2 * 4,                              # 4 radix passes over 16 B run records, read+write
+            "index_tuples_ms": hk * (0.5 + 12),                     # dp4 base read + (key, position) tuple write
+            "index_sort_ms": hk * 12 * 2,                            # one read + one write of every 12 B tuple (a single-pass partition)
+            "index_table_ms": hk * 8 + ctr["hash_kmers"] * 0,        # sorted keys read once (+ 32 B per distinct k-mer, not counted)
+            "probe_ms": rk * (0.5 + 32),                             # dp4 base + one 32 B slot sector per window
+            "expand_ms": sr * (4 + 16 + 16),                         # occurrence + bases compared + run record written
+            "sort_ms": sr * 16 * 2,                                  # one read + one write of every 16 B run record
             "chain_ms": sr * (16 + 12 + 12 + 16),
             "extend_ms": cells_step * 0.25,                          # 2-bit from-codes are the only HBM traffic per cell
         }[dom]

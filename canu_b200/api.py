@@ -57,7 +57,7 @@ class _Counters(C.Structure):
 
 class _Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
-        "upload_ms", "encode_ms", "index_count_ms", "index_scan_ms", "index_fill_ms", "index_skip_ms",
+        "upload_ms", "encode_ms", "index_tuples_ms", "index_sort_ms", "index_table_ms", "index_skip_ms",
         "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms", "download_ms", "total_ms")]
 
 

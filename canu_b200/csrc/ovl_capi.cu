@@ -36,7 +36,7 @@ int ovlb_device_count(void) {
 int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   if (!p || !out) { ovl_set_error("ovlb_create: null argument"); return OVLB_ERR_ARG; }
   *out = nullptr;
-  if (p->kmer_len < 2 || p->kmer_len > 31) { ovl_set_error("ovlb_create: kmer_len must be in 2..31"); return OVLB_ERR_ARG; }
+  if (p->kmer_len < 2 || p->kmer_len > 30) { ovl_set_error("ovlb_create: kmer_len must be in 2..30 (k-mer + 3 class bits + 1 sentinel bit must fit 64 bits)"); return OVLB_ERR_ARG; }
   if (!p->edit_match_limit || p->n_edit_match_limit < 2) { ovl_set_error("ovlb_create: edit_match_limit table missing"); return OVLB_ERR_ARG; }
   if (!(p->max_erate > 0.0) || p->max_erate >= 1.0) { ovl_set_error("ovlb_create: max_erate must be in (0,1)"); return OVLB_ERR_ARG; }
   if (p->max_read_len == 0 || p->max_read_len > OVLB_MAX_READLEN) { ovl_set_error("ovlb_create: max_read_len must be in 1..AS_MAX_READLEN"); return OVLB_ERR_ARG; }
@@ -90,9 +90,9 @@ void ovlb_destroy(ovlb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_reads(c->hash); free_reads(c->ref);
-  void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.keys, c->index.cnt, c->index.start, c->index.occ, c->index.slot_of,
+  void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.slots, c->index.occ, c->index.tkey, c->index.tkey2, c->index.tval,
                    c->ext.arena, c->ext.row_left, c->ext.row_off, c->ext.gring, c->ext.path, c->ext.ival, c->ext.ikc, c->ext.ldelta, c->ext.rdelta,
-                   c->d_packed, c->d_boff, c->d_nread, c->d_npos, c->ref_slot, c->ref_valid,
+                   c->d_packed, c->d_boff, c->d_nread, c->d_npos, c->ref_valid, c->item_small, c->item_large,
                    c->run_key, c->run_val, c->run_key2, c->run_val2, c->runs_extra, c->pair_flag, c->pair_idx, c->cub_temp, c->pairs,
                    c->seed_start, c->seed_off, c->seed_len, c->sim_nxt, c->sim_hits, c->sim_act, c->sim_order, c->seed_alive, c->d_records };
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -200,6 +200,9 @@ int ovlb_get_counters(ovlb_ctx *c, ovlb_counters *out) {
   out->extend_calls = h.v[CT_EXT_CALLS]; out->dp_cells = h.v[CT_DP_CELLS]; out->hash_kmers = h.v[CT_HASH_KMERS];
   out->ref_kmers = h.v[CT_REF_KMERS]; out->seed_hits = h.v[CT_SEED_HITS]; out->seed_runs = h.v[CT_SEED_RUNS];
   out->pairs = h.v[CT_PAIRS];
+  out->hash_kmers += c->host_counters[CT_HASH_KMERS];
+  out->ref_kmers  += c->host_counters[CT_REF_KMERS];
+  out->seed_runs  += c->host_counters[CT_SEED_RUNS];
   return OVLB_OK;
 }
 
@@ -209,6 +212,7 @@ int ovlb_reset_counters(ovlb_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemsetAsync(c->d_counters, 0, sizeof(DevCounters), c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  memset(c->host_counters, 0, sizeof(c->host_counters));
   return OVLB_OK;
 }
 

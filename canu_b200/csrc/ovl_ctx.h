@@ -16,6 +16,7 @@ struct DevReads {
   uint64_t  total_bases = 0;
   uint64_t  n_words = 0;          // dp4 words (incl. padding)
   uint64_t  n_pos = 0;            // 32-aligned position index space (sum of round_up(len,32))
+  uint64_t  n_windows = 0;        // sum of max(0, len-K+1): k-mer windows, one orientation
   uint32_t  max_len = 0;
   uint64_t *fwd = nullptr;        // dp4, forward
   uint64_t *rc  = nullptr;        // dp4, reverse complement
@@ -28,18 +29,23 @@ struct DevReads {
   size_t    cap_words = 0, cap_reads = 0, cap_groups = 0;
 };
 
-//  The k-mer index over the hash block: open-addressed (linear probing) table of distinct k-mers,
-//  each with the contiguous list of its occurrences (CSR).
+//  The k-mer index over the hash block: one 32-byte slot (= one DRAM sector) per DISTINCT k-mer in an
+//  open-addressed table (linear probing, load <= 0.5), pointing at the k-mer's occurrences in `occ`.
+//  The occurrences of a k-mer are contiguous and ordered by the class of the base that PRECEDES the
+//  occurrence in its hash read (0 = none: read start or N; 1..4 = A,C,G,T): class c is
+//  occ[c ? end[c-1] : start, end[c]).  Bit 63 of `key` marks a skip k-mer (the reference's Empty flag).
+#define OVL_SKIP_BIT (1ull << 63)
+struct __align__(32) IndexSlot { uint64_t key; uint32_t start; uint32_t end[5]; };
+
 struct DevIndex {
-  uint64_t  cap = 0;              // slots, power of two
-  uint64_t *keys = nullptr;       // [cap] k-mer (base j in bits 2j..2j+1) or OVL_EMPTY_KEY
-  uint32_t *cnt = nullptr;        // [cap] occurrences | OVL_SKIP_FLAG
-  uint32_t *start = nullptr;      // [cap] first entry in occ[]
-  uint64_t *occ = nullptr;        // [n_occ] (hash read index << 32) | offset
-  uint32_t *slot_of = nullptr;    // [hash n_pos] slot of the k-mer starting at each position (build scratch)
-  uint64_t  n_occ = 0;
-  bool      built = false;
-  size_t    cap_alloc = 0, occ_alloc = 0, slot_alloc = 0;
+  uint64_t   cap = 0;             // slots in use
+  IndexSlot *slots = nullptr;     // [cap]
+  uint32_t  *occ = nullptr;       // [n_occ] hash position index of each occurrence, sorted by (k-mer, class)
+  uint64_t   n_occ = 0, n_distinct = 0;
+  bool       built = false;
+  uint64_t  *tkey = nullptr, *tkey2 = nullptr;   // build scratch: (k-mer << 3 | class) before / after the sort
+  uint32_t  *tval = nullptr;                     // build scratch: position index before the sort
+  size_t     slots_cap = 0, occ_cap = 0, tkey_cap = 0, tkey2_cap = 0, tval_cap = 0;
 };
 
 struct DevCounters {              // mirrors ovlb_counters; device-resident, atomically updated
@@ -107,8 +113,8 @@ struct ovlb_ctx {
   std::vector<uint64_t> skip_keys;
 
   //  lookup products for the current ref batch
-  int32_t  *ref_slot = nullptr;   size_t ref_slot_cap = 0;    // [2 * ref.n_pos] slot or -1
-  uint32_t *ref_valid = nullptr;  size_t ref_valid_cap = 0;   // [2 * ref.n_pos / 32] bit set iff slot >= 0
+  uint32_t *ref_valid = nullptr;  size_t ref_valid_cap = 0;   // [2 * ref.n_pos / 32] bit set iff the window hits a non-skip k-mer
+  uint4    *item_small = nullptr, *item_large = nullptr;      // [run_cap] occurrence ranges holding run heads
   uint64_t *run_key = nullptr, *run_val = nullptr, *run_key2 = nullptr, *run_val2 = nullptr;
   uint64_t  run_cap = 0;
   OvlRun   *runs_extra = nullptr; size_t runs_extra_cap = 0;
@@ -121,7 +127,8 @@ struct ovlb_ctx {
   uint8_t  *seed_alive = nullptr;
   uint64_t  seed_cap = 0;
   ovlb_record *d_records = nullptr;  uint64_t rec_cap = 0;  uint64_t n_records = 0;
-  unsigned long long *d_work = nullptr;   // persistent-kernel work counters
+  unsigned long long *d_work = nullptr;   // [8] device-side cursors and counts
+  unsigned long long host_counters[16] = {0};   // counters known on the host (added to the device ones on readout)
 
   ovlb_timings timings;
   cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;     // ovlb_timer_start / ovlb_timer_stop

@@ -100,93 +100,168 @@ k_fill_groups(const uint64_t *__restrict__ pbase, uint32_t *__restrict__ grp_rea
 }
 
 // ------------------------------------------------------------------------------------------------
-//  k-mer of the window starting at base p (needs K <= 31): key with base j in bits [2j, 2j+1]
+//  k-mers of the 32 windows of one position group, computed by the whole warp.
+//
+//  Window p0+lane of the read whose dp4 words start at w (p0 a multiple of 32).  Lanes 0..4 load the five
+//  words that hold bases p0-16 .. p0+63 and convert them to 2-bit codes once; every lane then assembles its
+//  own 64-bit k-mer from three of them with two funnel shifts.  Returns false if the window runs past the
+//  end of the read or holds a base that is not ACGT.  `cls` is the class of the PRECEDING base:
+//  0 = none (start of read, or N), 1..4 = A,C,G,T.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool kmer_at(const uint64_t *__restrict__ w, int p, int K, uint64_t &key) {
-  uint32_t i0, i1;
-  uint64_t c0 = ovl_codes16(ovl_fetch16(w, p), &i0);
-  uint64_t c1 = ovl_codes16(ovl_fetch16(w, p + 16), &i1);
-  uint64_t all = c0 | (c1 << 32);
-  uint32_t inv = i0 | (i1 << 16);
-  key = all & ((1ull << (2 * K)) - 1);
-  return (inv & ((1u << K) - 1)) == 0;
+__device__ __forceinline__ bool warp_kmers(const uint64_t *__restrict__ w, int p0, int L, int K, int lane,
+                                           uint64_t &key, int &cls) {
+  uint32_t codes = 0, inv = 0xFFFFu;
+  if (lane < 5) {
+    const int idx = (p0 >> 4) - 1 + lane;
+    if (idx >= 0) codes = ovl_codes16(w[idx], &inv);
+  }
+  const int j0 = 1 + (lane >> 4);                      // first of my three words (word 0 = the one before p0)
+  const uint32_t cp = __shfl_sync(0xffffffffu, codes, j0 - 1), ip = __shfl_sync(0xffffffffu, inv, j0 - 1);
+  const uint32_t c0 = __shfl_sync(0xffffffffu, codes, j0),     i0 = __shfl_sync(0xffffffffu, inv, j0);
+  const uint32_t c1 = __shfl_sync(0xffffffffu, codes, j0 + 1), i1 = __shfl_sync(0xffffffffu, inv, j0 + 1);
+  const uint32_t c2 = __shfl_sync(0xffffffffu, codes, j0 + 2), i2 = __shfl_sync(0xffffffffu, inv, j0 + 2);
+  const int s = lane & 15;
+  const uint32_t lo = __funnelshift_r(c0, c1, 2 * s);
+  const uint32_t hi = __funnelshift_r(c1, c2, 2 * s);
+  key = (((uint64_t)hi << 32) | lo) & ((1ull << (2 * K)) - 1);
+  const uint64_t iv = ((uint64_t)i0 | ((uint64_t)i1 << 16) | ((uint64_t)i2 << 32)) >> s;
+  const int p = p0 + lane;
+  uint32_t pc, pi;
+  if (s > 0) { pc = (c0 >> (2 * (s - 1))) & 3u; pi = (i0 >> (s - 1)) & 1u; }
+  else       { pc = cp >> 30;                   pi = ip >> 15; }
+  cls = (p > 0 && pi == 0) ? (int)(1 + pc) : 0;
+  return (p + K <= L) && (((uint32_t)iv & ((1u << K) - 1)) == 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-//  K1: index build
+//  K1: index build = tuple generation -> radix sort -> one slot per distinct k-mer
+//
+//  Replaces Put_String_In_Hash / Hash_Insert / chain coalescing (Build_Hash_Index.C:267-404,613-628).
+//  Sorting (k-mer, class of the preceding base) groups the occurrences of a k-mer contiguously AND splits
+//  each group by the base that precedes the occurrence in its read; the lookup side needs exactly that to
+//  find the heads of diagonal runs without touching the occurrences that merely continue a run.
 // ------------------------------------------------------------------------------------------------
 
-//  one warp per 32-position group of the hash block; one k-mer per lane
+//  one warp per 32-position group of the hash block
 __global__ void __launch_bounds__(THREADS)
-k_index_count(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
+k_hash_tuples(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
               const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read, uint64_t n_groups,
-              int K, uint64_t *keys, uint32_t *cnt, uint64_t mask, uint32_t *__restrict__ slot_of,
-              unsigned long long *counters) {
+              int K, uint64_t *__restrict__ tkey, uint32_t *__restrict__ tval) {
   uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (g >= n_groups) return;
   const int lane = threadIdx.x & 31;
   const uint32_t r = grp_read[g];
   const int L = (int)len[r];
-  const int p = (int)(g * 32 - pbase[r]) + lane;
-  uint32_t slot = 0xFFFFFFFFu;
-  uint64_t key;
-  if (p + K <= L && kmer_at(fwd + woff[r], p, K, key)) {
-    uint64_t h = ovl_mix64(key) & mask;
-    while (true) {
-      uint64_t k = keys[h];
-      if (k == key) break;
-      if (k == OVL_EMPTY_KEY) {
-        unsigned long long old = atomicCAS((unsigned long long *)&keys[h], (unsigned long long)OVL_EMPTY_KEY, (unsigned long long)key);
-        if (old == OVL_EMPTY_KEY || old == key) break;
+  const int p0 = (int)(g * 32 - pbase[r]);
+  uint64_t key; int cls;
+  const bool ok = warp_kmers(fwd + woff[r], p0, L, K, lane, key, cls);
+  tkey[g * 32 + lane] = ok ? ((key << 3) | (uint64_t)cls) : (1ull << (2 * K + 3));     // invalid windows sort last
+  tval[g * 32 + lane] = (uint32_t)(g * 32 + lane);
+}
+
+//  counts distinct k-mers and finds the number of valid tuples in the sorted array
+#define CNT_PER_THREAD 8
+__global__ void __launch_bounds__(256)
+k_count_distinct(const uint64_t *__restrict__ skey, uint64_t n, uint64_t sentinel, unsigned long long *out /* [0] distinct, [1] n_occ */) {
+  __shared__ unsigned int blk;
+  if (threadIdx.x == 0) blk = 0;
+  __syncthreads();
+  const uint64_t base = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * CNT_PER_THREAD;
+  unsigned int c = 0;
+  uint64_t prev = (base > 0 && base <= n) ? skey[base - 1] : ~0ull;
+  #pragma unroll
+  for (int j = 0; j < CNT_PER_THREAD; j++) {
+    const uint64_t i = base + j;
+    if (i < n) {
+      const uint64_t k = skey[i];
+      if (k < sentinel) {
+        if (i == 0 || (k >> 3) != (prev >> 3)) c++;
+        if (i + 1 == n) out[1] = i + 1;
+      } else if (i == 0) {
+        out[1] = 0;
+      } else if (prev < sentinel) {
+        out[1] = i;
       }
-      h = (h + 1) & mask;
+      prev = k;
     }
-    atomicAdd(&cnt[h], 1u);
-    slot = (uint32_t)h;
   }
-  slot_of[g * 32 + lane] = slot;
-  unsigned m = __ballot_sync(0xffffffffu, slot != 0xFFFFFFFFu);
-  if (lane == 0 && m) atomicAdd(&counters[CT_HASH_KMERS], (unsigned long long)__popc(m));
+  if (c) atomicAdd(&blk, c);
+  __syncthreads();
+  if (threadIdx.x == 0 && blk) atomicAdd(&out[0], (unsigned long long)blk);
 }
 
-//  one thread per position: append the occurrence to its k-mer's list
-__global__ void __launch_bounds__(THREADS)
-k_index_fill(const uint32_t *__restrict__ slot_of, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
-             uint64_t n_pos, const uint32_t *__restrict__ start, uint32_t *cursor, uint64_t *__restrict__ occ) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pos) return;
-  uint32_t s = slot_of[i];
-  if (s == 0xFFFFFFFFu) return;
-  uint32_t r = grp_read[i >> 5];
-  uint32_t p = (uint32_t)(i - pbase[r]);
-  uint32_t o = atomicAdd(&cursor[s], 1u);
-  occ[(uint64_t)start[s] + o] = ((uint64_t)r << 32) | p;
+//  first index in [lo, n) whose key is >= target, galloping from lo (all keys before lo are < target)
+__device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restrict__ k, uint32_t lo, uint32_t n, uint64_t target) {
+  uint32_t hi = lo, step = 1;
+  while (hi < n && k[hi] < target) {
+    lo = hi + 1;
+    hi = (n - hi > step) ? hi + step : n;
+    step <<= 1;
+  }
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (k[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
 }
 
-//  one thread per skip k-mer: flag the slot (insert it if absent) and mark screened read ends
-__global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip, int K, uint64_t *keys, uint32_t *cnt,
-                             const uint32_t *__restrict__ start, uint64_t mask, const uint64_t *__restrict__ occ,
-                             const uint32_t *__restrict__ hlen, uint32_t *hflags) {
+__device__ __forceinline__ uint64_t slot_home(uint64_t key, uint64_t cap) { return __umul64hi(ovl_mix64(key), cap); }
+
+//  find the slot of `key`, inserting it if absent; returns the slot index
+__device__ __forceinline__ uint64_t slot_find_or_insert(IndexSlot *slots, uint64_t cap, uint64_t key) {
+  uint64_t h = slot_home(key, cap);
+  while (true) {
+    unsigned long long *kp = (unsigned long long *)&slots[h].key;
+    unsigned long long k = *(volatile unsigned long long *)kp;
+    if ((k & ~OVL_SKIP_BIT) == key && k != OVL_EMPTY_KEY) return h;
+    if (k == OVL_EMPTY_KEY) {
+      unsigned long long old = atomicCAS(kp, (unsigned long long)OVL_EMPTY_KEY, (unsigned long long)key);
+      if (old == OVL_EMPTY_KEY || ((old & ~OVL_SKIP_BIT) == key)) return h;
+    }
+    h = (h + 1 == cap) ? 0 : h + 1;
+  }
+}
+
+//  one thread per sorted tuple; the first tuple of every k-mer builds the k-mer's slot
+__global__ void __launch_bounds__(256)
+k_build_slots(const uint64_t *__restrict__ skey, uint32_t n_occ, IndexSlot *slots, uint64_t cap) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_occ) return;
+  const uint64_t k = skey[i];
+  if (i > 0 && (skey[i - 1] >> 3) == (k >> 3)) return;
+  const uint64_t kmer = k >> 3;
+  uint32_t e[5];
+  uint32_t lo = (uint32_t)i;
+  #pragma unroll
+  for (int c = 0; c < 5; c++) {
+    lo = gallop_lower_bound(skey, lo, n_occ, (kmer << 3) + (uint64_t)(c + 1));
+    e[c] = lo;
+  }
+  const uint64_t h = slot_find_or_insert(slots, cap, kmer);
+  uint4 *sp = reinterpret_cast<uint4 *>(&slots[h]);
+  //  the key half was written by the CAS; fill in the rest (no other thread writes this slot)
+  slots[h].start = (uint32_t)i;
+  slots[h].end[0] = e[0];
+  sp[1] = make_uint4(e[1], e[2], e[3], e[4]);
+}
+
+//  one thread per skip k-mer: flag the slot (insert it if absent, Add_Extra_Hash_String) and mark screened read ends
+__global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip, int K, IndexSlot *slots, uint64_t cap,
+                             const uint32_t *__restrict__ occ, const uint64_t *__restrict__ hpbase,
+                             const uint32_t *__restrict__ hgrp_read, const uint32_t *__restrict__ hlen, uint32_t *hflags) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_skip) return;
-  uint64_t key = skip[i];
-  uint64_t h = ovl_mix64(key) & mask;
-  while (true) {
-    uint64_t k = keys[h];
-    if (k == key) break;
-    if (k == OVL_EMPTY_KEY) {
-      unsigned long long old = atomicCAS((unsigned long long *)&keys[h], (unsigned long long)OVL_EMPTY_KEY, (unsigned long long)key);
-      if (old == OVL_EMPTY_KEY || old == key) break;
-    }
-    h = (h + 1) & mask;
-  }
-  uint32_t c = atomicOr(&cnt[h], OVL_SKIP_FLAG);
-  if (c & OVL_SKIP_FLAG) return;                        // duplicate in the skip list: already handled
-  uint32_t n = c & ~OVL_SKIP_FLAG;
-  uint64_t st = start[h];
-  for (uint32_t j = 0; j < n; j++) {                     // Mark_Screened_Ends_Chain (Build_Hash_Index.C:98-121)
-    uint64_t e = occ[st + j];
-    uint32_t r = (uint32_t)(e >> 32), q = (uint32_t)e;
+  const uint64_t key = skip[i];
+  const uint64_t h = slot_find_or_insert(slots, cap, key);
+  const unsigned long long old = atomicOr((unsigned long long *)&slots[h].key, (unsigned long long)OVL_SKIP_BIT);
+  if (old & OVL_SKIP_BIT) return;                        // duplicate in the skip list: already handled
+  //  a slot inserted just now by this kernel has start/end still 0xFFFFFFFF: an absent k-mer, empty list
+  const uint32_t st = slots[h].start, en = slots[h].end[4];
+  if (st == 0xFFFFFFFFu) { slots[h].start = 0; slots[h].end[0] = 0; reinterpret_cast<uint4 *>(&slots[h])[1] = make_uint4(0, 0, 0, 0); return; }
+  for (uint32_t j = st; j < en; j++) {                   // Mark_Screened_Ends_Chain (Build_Hash_Index.C:98-121)
+    const uint32_t pos = occ[j];
+    const uint32_t r = hgrp_read[pos >> 5];
+    const uint32_t q = (uint32_t)(pos - hpbase[r]);
     uint32_t f = 0;
     if (q < OVL_HOPELESS_MATCH) f |= 1u;
     if ((int)hlen[r] - (int)q - K + 1 < OVL_HOPELESS_MATCH) f |= 2u;
@@ -195,14 +270,64 @@ __global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip,
 }
 
 // ------------------------------------------------------------------------------------------------
-//  K2a: probe every ref window (both orientations)
+//  K2a: probe every ref window (both orientations); emit the occurrence ranges that hold run heads
+//
+//  Replaces the window loop of Find_Overlaps + Hash_Find (Find_Overlaps.C:177-336).  A hit (p, q) on hash
+//  read h continues the diagonal run of hit (p-1, q-1) iff window p-1 is itself a hit window and
+//  h[q-1] == ref[p-1]; Add_Match folds such hits into the existing Match_Node (Find_Overlaps.C:45-55).
+//  The occurrence list of a k-mer is split by h[q-1], so the hits that START a run are the occurrences in
+//  the classes other than ref[p-1] (all of them when window p-1 is not a hit window).  Only those ranges
+//  are passed on; on real read sets they are a small fraction of the list.
 // ------------------------------------------------------------------------------------------------
+struct SlotView { bool found, skip; uint32_t start, e0, e1, e2, e3, e4; };
+
+__device__ __forceinline__ SlotView slot_lookup(const IndexSlot *__restrict__ slots, uint64_t cap, uint64_t key) {
+  SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
+  uint64_t h = slot_home(key, cap);
+  while (true) {
+    const uint4 *sp = reinterpret_cast<const uint4 *>(slots + h);
+    const uint4 a = __ldg(sp), b = __ldg(sp + 1);
+    const uint64_t k = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    if (k == OVL_EMPTY_KEY) return v;
+    if ((k & ~OVL_SKIP_BIT) == key) {
+      v.found = true; v.skip = (k & OVL_SKIP_BIT) != 0;
+      v.start = a.z; v.e0 = a.w; v.e1 = b.x; v.e2 = b.y; v.e3 = b.z; v.e4 = b.w;
+      return v;
+    }
+    h = (h + 1 == cap) ? 0 : h + 1;
+  }
+}
+
+#define SMALL_ITEM_MAX 8u
+
+//  item = (ref position index, first occurrence, count << 1 | dir)
+__device__ __forceinline__ void emit_items(bool has, uint32_t pos, uint32_t begin, uint32_t count, int dir, int lane,
+                                           uint4 *__restrict__ small, uint4 *__restrict__ large, uint64_t item_cap,
+                                           unsigned long long *n_small, unsigned long long *n_large) {
+  const bool sm = has && count <= SMALL_ITEM_MAX, lg = has && count > SMALL_ITEM_MAX;
+  const unsigned ms = __ballot_sync(0xffffffffu, sm), ml = __ballot_sync(0xffffffffu, lg);
+  if (ms) {
+    unsigned long long base = 0;
+    const int leader = __ffs(ms) - 1;
+    if (lane == leader) base = atomicAdd(n_small, (unsigned long long)__popc(ms));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (sm) { const unsigned long long idx = base + __popc(ms & ((1u << lane) - 1)); if (idx < item_cap) small[idx] = make_uint4(pos, begin, (count << 1) | (uint32_t)dir, 0); }
+  }
+  if (ml) {
+    unsigned long long base = 0;
+    const int leader = __ffs(ml) - 1;
+    if (lane == leader) base = atomicAdd(n_large, (unsigned long long)__popc(ml));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (lg) { const unsigned long long idx = base + __popc(ml & ((1u << lane) - 1)); if (idx < item_cap) large[idx] = make_uint4(pos, begin, (count << 1) | (uint32_t)dir, 0); }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS)
 k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, const uint64_t *__restrict__ woff,
             const uint32_t *__restrict__ len, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
-            uint64_t n_groups, uint64_t n_pos, int K, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ cnt,
-            uint64_t mask, int32_t *__restrict__ ref_slot, uint32_t *__restrict__ ref_valid, uint32_t *rflags,
-            unsigned long long *counters) {
+            uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint64_t cap,
+            uint32_t *__restrict__ ref_valid, uint32_t *rflags,
+            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work) {
   uint64_t gg = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (gg >= 2 * n_groups) return;
   const int lane = threadIdx.x & 31;
@@ -210,153 +335,175 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
   const uint64_t g = dir ? gg - n_groups : gg;
   const uint32_t r = grp_read[g];
   const int L = (int)len[r];
-  const int p = (int)(g * 32 - pbase[r]) + lane;
+  const int p0 = (int)(g * 32 - pbase[r]);
+  const int p = p0 + lane;
   const uint64_t *w = (dir ? rc : fwd) + woff[r];
-  int32_t slot = -1;
-  bool inrange = (p + K <= L);
-  uint64_t key;
-  if (inrange && kmer_at(w, p, K, key)) {
-    uint64_t h = ovl_mix64(key) & mask;
-    while (true) {
-      uint64_t k = keys[h];
-      if (k == key) {
-        uint32_t c = cnt[h];
-        if (c & OVL_SKIP_FLAG) {                          // hi_hits (Find_Overlaps.C:274-276,310-316)
-          uint32_t f = 0;
-          if (p == 0) f = 1u;
-          else {
-            if (p < OVL_HOPELESS_MATCH) f |= 1u;
-            if (L - p - K + 1 < OVL_HOPELESS_MATCH) f |= 2u;
-          }
-          if (f) atomicOr(&rflags[2 * r + dir], f);
-        } else if (c != 0) {
-          slot = (int32_t)h;
-        }
-        break;
-      }
-      if (k == OVL_EMPTY_KEY) break;
-      h = (h + 1) & mask;
+
+  uint64_t key; int cls;
+  const bool ok = warp_kmers(w, p0, L, K, lane, key, cls);
+  SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
+  if (ok) v = slot_lookup(slots, cap, key);
+  if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
+    uint32_t f = 0;
+    if (p == 0) f = 1u;
+    else {
+      if (p < OVL_HOPELESS_MATCH) f |= 1u;
+      if (L - p - K + 1 < OVL_HOPELESS_MATCH) f |= 2u;
+    }
+    if (f) atomicOr(&rflags[2 * r + dir], f);
+  }
+  const bool valid = v.found && !v.skip && v.e4 > v.start;
+  const unsigned vm = __ballot_sync(0xffffffffu, valid);
+  if (lane == 0) ref_valid[((uint64_t)dir * n_pos >> 5) + g] = vm;
+  if (vm == 0) return;
+
+  //  is window p-1 a hit window?  lanes 1..31 see it in the ballot; lane 0 looks window p0-1 up itself
+  bool prev_valid = (lane > 0) && ((vm >> (lane - 1)) & 1u);
+  if (lane == 0 && valid && p0 > 0 && cls != 0) {
+    //  k-mer of window p0-1 = my k-mer shifted up one base with ref[p0-1] in front (it cannot contain an N:
+    //  its last K-1 bases are mine and cls != 0 says base p0-1 is ACGT)
+    const uint64_t pk = ((key << 2) | (uint64_t)(cls - 1)) & ((1ull << (2 * K)) - 1);
+    const SlotView pv = slot_lookup(slots, cap, pk);
+    prev_valid = pv.found && !pv.skip && pv.e4 > pv.start;
+  }
+
+  //  head ranges: the whole list, or the list minus the class of ref[p-1]
+  uint32_t b0 = v.start, n0 = 0, b1 = 0, n1 = 0;
+  if (valid) {
+    if (prev_valid && cls != 0) {
+      const uint32_t lo = (cls == 1) ? v.e0 : (cls == 2) ? v.e1 : (cls == 3) ? v.e2 : v.e3;     // start of class cls
+      const uint32_t hi = (cls == 1) ? v.e1 : (cls == 2) ? v.e2 : (cls == 3) ? v.e3 : v.e4;     // end of class cls
+      n0 = lo - v.start; b1 = hi; n1 = v.e4 - hi;
+    } else {
+      n0 = v.e4 - v.start;
     }
   }
-  ref_slot[(uint64_t)dir * n_pos + g * 32 + lane] = slot;
-  unsigned vm = __ballot_sync(0xffffffffu, slot >= 0);
-  unsigned im = __ballot_sync(0xffffffffu, inrange);
-  if (lane == 0) {
-    ref_valid[((uint64_t)dir * n_pos >> 5) + g] = vm;
-    if (im) atomicAdd(&counters[CT_REF_KMERS], (unsigned long long)__popc(im));
+  const uint32_t pos = (uint32_t)(g * 32 + lane);
+  if (__any_sync(0xffffffffu, n0 | n1)) {
+    emit_items(n0 > 0, pos, b0, n0, dir, lane, item_small, item_large, item_cap, &work[3], &work[4]);
+    emit_items(n1 > 0, pos, b1, n1, dir, lane, item_small, item_large, item_cap, &work[3], &work[4]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-//  K2b: expand hits, keep only the first hit of every maximal diagonal run, emit (key, value) runs
+//  K2b: turn head occurrences into seed runs (Add_Ref + the node-creating branch of Add_Match,
+//  Find_Overlaps.C:61-86,105-163): ID filter, run length, warp-aggregated append of (key, value)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS)
-k_ref_expand(const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff,
-             const uint32_t *__restrict__ rlen, const uint64_t *__restrict__ rpbase, const uint32_t *__restrict__ grp_read,
-             uint64_t n_groups, uint64_t n_pos, uint32_t ref_first_id,
-             const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hwoff, const uint32_t *__restrict__ hlen,
-             uint32_t hash_first_id, int K,
-             const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ start, const uint64_t *__restrict__ occ,
-             const int32_t *__restrict__ ref_slot, const uint32_t *__restrict__ ref_valid,
-             uint64_t *__restrict__ run_key, uint64_t *__restrict__ run_val, uint64_t run_cap,
-             unsigned long long *n_runs, unsigned long long *counters) {
-  uint64_t gg = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (gg >= 2 * n_groups) return;
-  const int lane = threadIdx.x & 31;
-  const int dir = gg >= n_groups;
-  const uint64_t g = dir ? gg - n_groups : gg;
-  const uint64_t vword = ((uint64_t)dir * n_pos >> 5) + g;
-  const uint32_t vw = ref_valid[vword];
-  if (vw == 0) return;
+struct ExpandArgs {
+  const uint64_t *rfwd, *rrc, *rwoff; const uint32_t *rlen; const uint64_t *rpbase; const uint32_t *rgrp_read;
+  uint64_t r_npos; uint32_t ref_first_id;
+  const uint64_t *hfwd, *hwoff; const uint32_t *hlen; const uint64_t *hpbase; const uint32_t *hgrp_read; uint32_t hash_first_id;
+  int K;
+  const uint32_t *occ; const uint32_t *ref_valid;
+  uint64_t *run_key, *run_val; uint64_t run_cap;
+  unsigned long long *n_runs;
+};
 
-  const uint32_t r = grp_read[g];
-  const int L = (int)rlen[r];
-  const int p0 = (int)(g * 32 - rpbase[r]);
-  const uint64_t *rw = (dir ? rrc : rfwd) + rwoff[r];
-  const uint32_t ref_id = ref_first_id + r;
-  const uint32_t prev_top = (p0 > 0) ? (ref_valid[vword - 1] >> 31) : 0u;
-
-  const int32_t my_slot = ref_slot[(uint64_t)dir * n_pos + g * 32 + lane];
-  uint32_t my_cnt = 0, my_start = 0;
-  if (my_slot >= 0) { my_cnt = cnt[my_slot] & ~OVL_SKIP_FLAG; my_start = start[my_slot]; }
-
-  unsigned long long hits_acc = 0, runs_acc = 0;
-
-  for (uint32_t bits = vw; bits; bits &= bits - 1) {
-    const int b = __ffs(bits) - 1;
-    const int p = p0 + b;
-    const uint32_t c  = __shfl_sync(0xffffffffu, my_cnt, b);
-    const uint32_t st = __shfl_sync(0xffffffffu, my_start, b);
-    const bool prev_valid = (b > 0) ? ((vw >> (b - 1)) & 1u) : (prev_top != 0);
-    const uint32_t ref_prev_nib = (p > 0) ? ovl_nibble(rw, p - 1) : 0u;
-
-    for (uint32_t j0 = 0; j0 < c; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      bool is_start = false;
-      uint32_t hh = 0, q = 0, runlen = 0;
-      if (j < c) {
-        uint64_t e = occ[(uint64_t)st + j];
-        hh = (uint32_t)(e >> 32); q = (uint32_t)e;
-        if (ref_id < hash_first_id + hh) {                 // only refID < hashID pairs (Find_Overlaps.C:279,320)
-          const uint64_t *hw = hfwd + hwoff[hh];
-          is_start = true;
-          if (prev_valid && q > 0 && ovl_nibble(hw, (int)q - 1) == ref_prev_nib) is_start = false;
-          if (is_start) {
-            //  run length: equal bases after the k-mer, and consecutive valid ref windows
-            const int HL = (int)hlen[hh];
-            int lim = min(L - (p + K), HL - ((int)q + K));
-            int e2 = 0;
-            while (e2 < lim) {
-              int k = ovl_equal16(ovl_fetch16(rw, p + K + e2), ovl_fetch16(hw, (int)q + K + e2));
-              e2 += k;
-              if (k < 16) break;
-            }
-            if (e2 > lim) e2 = lim;
-            int want = e2 + 1;
-            uint32_t rem = vw >> b;
-            int nv = __ffs(~rem) - 1;                       // ones run inside this word (<= 32-b)
-            if (nv < 0) nv = 32;
-            if (nv == 32 - b) {
-              uint64_t wi = vword + 1;
-              while (nv < want) {
-                uint32_t x = ref_valid[wi++];
-                if (x == 0xFFFFFFFFu) { nv += 32; continue; }
-                nv += __ffs(~x) - 1;
-                break;
-              }
-            }
-            runlen = (uint32_t)min(want, nv);
-          }
-        }
-      }
-      unsigned m = __ballot_sync(0xffffffffu, is_start);
-      if (m) {
-        unsigned long long base = 0;
-        int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(n_runs, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (is_start) {
-          unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
-          if (idx < run_cap) {
-            run_key[idx] = ovl_runkey(r, (uint32_t)dir, hh, (uint32_t)p);
-            run_val[idx] = (uint64_t)q | ((uint64_t)runlen << 32);
-          }
-          hits_acc += runlen;
-          runs_acc += 1;
-        }
-      }
+//  one head occurrence: returns true and fills (key, val, runlen) if it yields a run
+__device__ __forceinline__ bool head_to_run(const ExpandArgs &A, uint32_t pos, int dir, uint32_t hpos, uint64_t &rkey, uint64_t &rval, uint32_t &runlen) {
+  const uint32_t r = A.rgrp_read[pos >> 5];
+  const uint32_t hh = A.hgrp_read[hpos >> 5];
+  if (A.ref_first_id + r >= A.hash_first_id + hh) return false;          // only refID < hashID pairs (Find_Overlaps.C:279,320)
+  const int p = (int)(pos - A.rpbase[r]);
+  const int q = (int)(hpos - A.hpbase[hh]);
+  const int L = (int)A.rlen[r], HL = (int)A.hlen[hh];
+  const uint64_t *rw = (dir ? A.rrc : A.rfwd) + A.rwoff[r];
+  const uint64_t *hw = A.hfwd + A.hwoff[hh];
+  //  run length: equal bases after the k-mer ...
+  const int lim = min(L - (p + A.K), HL - (q + A.K));
+  int e2 = 0;
+  while (e2 < lim) {
+    const int k = ovl_equal16(ovl_fetch16(rw, p + A.K + e2), ovl_fetch16(hw, q + A.K + e2));
+    e2 += k;
+    if (k < 16) break;
+  }
+  if (e2 > lim) e2 = lim;
+  const int want = e2 + 1;
+  //  ... and consecutive hit windows on the ref side (a skip k-mer or an N ends the run)
+  const uint64_t vbase = (uint64_t)dir * A.r_npos;
+  uint64_t wi = (vbase + pos) >> 5;
+  const int b = (int)(pos & 31);
+  const uint32_t rem = A.ref_valid[wi] >> b;
+  int nv = __ffs(~rem) - 1;
+  if (nv < 0 || nv > 32 - b) nv = 32 - b;
+  if (nv == 32 - b) {
+    wi++;
+    while (nv < want) {
+      const uint32_t x = A.ref_valid[wi++];
+      if (x == 0xFFFFFFFFu) { nv += 32; continue; }
+      nv += __ffs(~x) - 1;
+      break;
     }
   }
-  //  warp totals
+  runlen = (uint32_t)min(want, nv);
+  rkey = ovl_runkey(r, (uint32_t)dir, hh, (uint32_t)p);
+  rval = (uint64_t)(uint32_t)q | ((uint64_t)runlen << 32);
+  return true;
+}
+
+__device__ __forceinline__ void append_run(const ExpandArgs &A, bool has, uint64_t rkey, uint64_t rval, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (!m) return;
+  unsigned long long base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(A.n_runs, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (has) {
+    const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
+    if (idx < A.run_cap) { A.run_key[idx] = rkey; A.run_val[idx] = rval; }
+  }
+}
+
+//  thread per item, items of at most SMALL_ITEM_MAX occurrences
+__global__ void __launch_bounds__(256)
+k_expand_small(ExpandArgs A, const uint4 *__restrict__ items, const unsigned long long *n_items_p, uint64_t item_cap,
+               unsigned long long *counters) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long n_items = *n_items_p; if (n_items > item_cap) n_items = item_cap;
+  unsigned long long hits = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_round = (n_items + 31) & ~31ull;      // whole warps stay together for the ballots
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    uint4 it = make_uint4(0, 0, 0, 0);
+    if (i < n_items) it = items[i];
+    const uint32_t cnt = it.z >> 1; const int dir = (int)(it.z & 1u);
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+    for (uint32_t j = 0; j < mx; j++) {
+      uint64_t rk = 0, rv = 0; uint32_t rl = 0;
+      bool has = false;
+      if (j < cnt) has = head_to_run(A, it.x, dir, A.occ[it.y + j], rk, rv, rl);
+      if (has) hits += rl;
+      append_run(A, has, rk, rv, lane);
+    }
+  }
   #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    hits_acc += __shfl_down_sync(0xffffffffu, hits_acc, o);
-    runs_acc += __shfl_down_sync(0xffffffffu, runs_acc, o);
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
+  if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
+}
+
+//  warp per item
+__global__ void __launch_bounds__(256)
+k_expand_large(ExpandArgs A, const uint4 *__restrict__ items, const unsigned long long *n_items_p, uint64_t item_cap,
+               unsigned long long *counters) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long n_items = *n_items_p; if (n_items > item_cap) n_items = item_cap;
+  unsigned long long hits = 0;
+  const uint64_t wstride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_items; i += wstride) {
+    const uint4 it = items[i];
+    const uint32_t cnt = it.z >> 1; const int dir = (int)(it.z & 1u);
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      uint64_t rk = 0, rv = 0; uint32_t rl = 0;
+      bool has = false;
+      if (j < cnt) has = head_to_run(A, it.x, dir, A.occ[it.y + j], rk, rv, rl);
+      if (has) hits += rl;
+      append_run(A, has, rk, rv, lane);
+    }
   }
-  if (lane == 0 && runs_acc) {
-    atomicAdd(&counters[CT_SEED_HITS], hits_acc);
-    atomicAdd(&counters[CT_SEED_RUNS], runs_acc);
-  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
+  if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -497,7 +644,8 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   if (!in || (in->n_reads && (!in->byte_offset || !in->len))) { ovl_set_error("ovl_upload_reads: null argument"); return OVLB_ERR_ARG; }
   const uint32_t n = in->n_reads;
   std::vector<uint64_t> woff(n + 1), pbase(n + 1);
-  uint64_t nw = 0, np = 0, tb = 0; uint32_t maxlen = 0;
+  uint64_t nw = 0, np = 0, tb = 0, nwin = 0; uint32_t maxlen = 0;
+  const uint32_t K = c->P.kmer_len;
   for (uint32_t i = 0; i < n; i++) {
     woff[i] = nw; pbase[i] = np;
     uint32_t L = in->len[i];
@@ -505,6 +653,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
     nw += (uint64_t)(L + 15) / 16 + 2;
     np += ((uint64_t)L + 31) / 32 * 32;
     tb += L;
+    if (L >= K) nwin += L - K + 1;
     if (L > maxlen) maxlen = L;
   }
   woff[n] = nw; pbase[n] = np;
@@ -529,7 +678,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
     CK(cudaMalloc((void **)&dst.flags, want * 8));       // 2 x uint32 per read
     dst.cap_reads = want;
   }
-  dst.n = n; dst.first_id = in->first_read_id; dst.total_bases = tb; dst.n_words = nw; dst.n_pos = np; dst.max_len = maxlen;
+  dst.n = n; dst.first_id = in->first_read_id; dst.total_bases = tb; dst.n_words = nw; dst.n_pos = np; dst.n_windows = nwin; dst.max_len = maxlen;
 
   EvTimer tu(c->stream);
   if ((rc = ensure(c->d_packed, c->packed_cap, (size_t)in->packed_bytes + 16))) return rc;
@@ -580,67 +729,68 @@ int ovl_build_index(ovlb_ctx *c) {
   int rc;
   const int K = (int)c->P.kmer_len;
   const uint64_t n_groups = H.n_pos / 32;
+  const uint64_t n = H.n_pos;
+  const uint64_t sentinel = 1ull << (2 * K + 3);
 
-  //  capacity: at most one distinct k-mer per base, load factor <= 0.5, plus the skip list
-  uint64_t want = 2 * (H.total_bases + c->skip_keys.size()) + 1024;
-  uint64_t cap = 1024; while (cap < want) cap <<= 1;
-  if (cap > X.cap_alloc) {
-    if (X.keys) cudaFree(X.keys); if (X.cnt) cudaFree(X.cnt); if (X.start) cudaFree(X.start);
-    X.keys = nullptr; X.cnt = nullptr; X.start = nullptr; X.cap_alloc = 0;
-    CK(cudaMalloc((void **)&X.keys, cap * 8));
-    CK(cudaMalloc((void **)&X.cnt, cap * 4));
-    CK(cudaMalloc((void **)&X.start, cap * 4));
-    X.cap_alloc = cap;
-  }
-  X.cap = cap;
-  if ((rc = ensure(X.slot_of, X.slot_alloc, (size_t)H.n_pos + 32))) return rc;
   if ((rc = ensure_groups(c, H))) return rc;
+  if ((rc = ensure(X.tkey, X.tkey_cap, (size_t)n + 32))) return rc;
+  if ((rc = ensure(X.tkey2, X.tkey2_cap, (size_t)n + 32))) return rc;
+  if ((rc = ensure(X.tval, X.tval_cap, (size_t)n + 32))) return rc;
+  if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
 
+  //  (k-mer, class of the preceding base) -> position, one tuple per window
   EvTimer t1(c->stream);
-  CK(cudaMemsetAsync(X.keys, 0xFF, cap * 8, c->stream));
-  CK(cudaMemsetAsync(X.cnt, 0, cap * 4, c->stream));
   if (n_groups) {
-    k_index_count<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(
-        H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.keys, X.cnt, cap - 1, X.slot_of, c->d_counters->v);
+    k_hash_tuples<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.tkey, X.tval);
     c->launches++;
   }
   CK(cudaGetLastError());
-  c->timings.index_count_ms = t1.stop();
+  c->timings.index_tuples_ms = t1.stop();
 
   EvTimer t2(c->stream);
-  size_t tb = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb, X.cnt, X.start, (int64_t)cap, c->stream);
-  if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
-  size_t tb2 = c->cub_temp_cap;
-  CK(cub::DeviceScan::ExclusiveSum(c->cub_temp, tb2, X.cnt, X.start, (int64_t)cap, c->stream));
-  c->launches += 2;
-  unsigned long long hk = 0;
-  CK(cudaMemcpyAsync(&hk, &c->d_counters->v[CT_HASH_KMERS], 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  //  CT_HASH_KMERS is cumulative over the context; the occurrences of THIS block are start[cap-1]+cnt[cap-1]
-  uint32_t last_start = 0, last_cnt = 0;
-  CK(cudaMemcpy(&last_start, X.start + (cap - 1), 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(&last_cnt, X.cnt + (cap - 1), 4, cudaMemcpyDeviceToHost));
-  X.n_occ = (uint64_t)last_start + last_cnt;
-  c->timings.index_scan_ms = t2.stop();
-
-  if ((rc = ensure(X.occ, X.occ_alloc, (size_t)X.n_occ + 32))) return rc;
+  if (n) {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream);
+    if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
+    size_t tb2 = c->cub_temp_cap;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream));
+    c->launches += 2 + (2 * K + 4 + 7) / 8;
+  }
+  CK(cudaGetLastError());
+  c->timings.index_sort_ms = t2.stop();
 
   EvTimer t3(c->stream);
-  CK(cudaMemsetAsync(X.cnt, 0, cap * 4, c->stream));
-  if (H.n_pos) {
-    k_index_fill<<<div_up(H.n_pos, THREADS), THREADS, 0, c->stream>>>(X.slot_of, H.pbase, H.grp_read, H.n_pos, X.start, X.cnt, X.occ);
+  unsigned long long h2[2] = {0, 0};
+  CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
+  if (n) {
+    k_count_distinct<<<div_up(n, 256 * CNT_PER_THREAD), 256, 0, c->stream>>>(X.tkey2, n, sentinel, &c->d_work[5]);
+    c->launches++;
+  }
+  CK(cudaMemcpyAsync(h2, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  X.n_distinct = h2[0];
+  X.n_occ = h2[1];
+
+  //  one 32-byte slot per distinct k-mer (and per skip k-mer), load factor <= 0.5
+  uint64_t cap = 2 * (X.n_distinct + c->skip_keys.size()) + 64;
+  if ((rc = ensure(X.slots, X.slots_cap, (size_t)cap, 9, 8))) return rc;
+  X.cap = cap;
+  CK(cudaMemsetAsync(X.slots, 0xFF, cap * sizeof(IndexSlot), c->stream));
+  if (X.n_occ) {
+    k_build_slots<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, (uint32_t)X.n_occ, X.slots, cap);
     c->launches++;
   }
   CK(cudaGetLastError());
-  c->timings.index_fill_ms = t3.stop();
+  c->timings.index_table_ms = t3.stop();
+  c->host_counters[CT_HASH_KMERS] += X.n_occ;
 
   EvTimer t4(c->stream);
   if (!c->skip_keys.empty()) {
     uint64_t *d_skip = nullptr;
     CK(cudaMalloc((void **)&d_skip, c->skip_keys.size() * 8));
     CK(cudaMemcpyAsync(d_skip, c->skip_keys.data(), c->skip_keys.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    k_index_skip<<<div_up(c->skip_keys.size(), 128), 128, 0, c->stream>>>(d_skip, c->skip_keys.size(), K, X.keys, X.cnt, X.start, cap - 1, X.occ, H.len, H.flags);
+    k_index_skip<<<div_up(c->skip_keys.size(), 128), 128, 0, c->stream>>>(d_skip, c->skip_keys.size(), K, X.slots, cap, X.occ,
+                                                                          H.pbase, H.grp_read, H.len, H.flags);
     c->launches++;
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(d_skip);
@@ -662,56 +812,67 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
   if (R.n >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   if (H.n >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); split it"); return OVLB_ERR_CAPACITY; }
 
-  if ((rc = ensure(c->ref_slot, c->ref_slot_cap, (size_t)2 * R.n_pos + 64))) return rc;
   if ((rc = ensure(c->ref_valid, c->ref_valid_cap, (size_t)2 * n_groups + 8))) return rc;
   if ((rc = ensure_groups(c, R))) return rc;
 
-  CK(cudaMemsetAsync(c->d_work, 0, 64, c->stream));       // [0] n_runs, [1] extend work cursor, [2] n_records
-  CK(cudaMemsetAsync(R.flags, 0, (size_t)(R.n + 1) * 8, c->stream));
-
-  EvTimer t1(c->stream);
-  if (n_groups) {
-    k_ref_probe<<<div_up(2 * n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(
-        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.keys, X.cnt, X.cap - 1,
-        c->ref_slot, c->ref_valid, R.flags, c->d_counters->v);
-    c->launches++;
-  }
-  CK(cudaGetLastError());
-  c->timings.probe_ms = t1.stop();
-
-  //  run buffers: sized from the memory budget once; overflow -> OVLB_ERR_CAPACITY
+  //  run and item buffers: sized from the memory budget once; overflow -> OVLB_ERR_CAPACITY
   if (c->run_cap == 0) {
-    uint64_t want = c->mem_budget / 12 / 56;               // ~1/12 of the budget over 56 B/run of run-side arrays
+    uint64_t want = c->mem_budget / 12 / 88;               // ~1/12 of the budget over 88 B/run of run-side arrays
     if (want < (1u << 20)) want = 1u << 20;
     if (want > (1ull << 31)) want = 1ull << 31;
-    size_t cap0 = 0, cap1 = 0, cap2 = 0, cap3 = 0;
+    size_t cap0 = 0, cap1 = 0, cap2 = 0, cap3 = 0, cap4 = 0, cap5 = 0;
     if ((rc = ensure(c->run_key, cap0, want, 1, 1))) return rc;
     if ((rc = ensure(c->run_val, cap1, want, 1, 1))) return rc;
     if ((rc = ensure(c->run_key2, cap2, want, 1, 1))) return rc;
     if ((rc = ensure(c->run_val2, cap3, want, 1, 1))) return rc;
+    if ((rc = ensure(c->item_small, cap4, want, 1, 1))) return rc;
+    if ((rc = ensure(c->item_large, cap5, want, 1, 1))) return rc;
     c->run_cap = want;
   }
 
-  EvTimer t2(c->stream);
+  CK(cudaMemsetAsync(c->d_work, 0, 40, c->stream));       // [0] n_runs, [1] extend work cursor, [2] n_records, [3] small items, [4] large items
+  CK(cudaMemsetAsync(R.flags, 0, (size_t)(R.n + 1) * 8, c->stream));
+  CK(cudaMemsetAsync(c->ref_valid + 2 * n_groups, 0, 32, c->stream));     // the run-length scan may peek one word past the end
+
+  EvTimer t1(c->stream);
   if (n_groups) {
-    k_ref_expand<<<div_up(2 * n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(
-        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, R.first_id,
-        H.fwd, H.woff, H.len, H.first_id, K, X.cnt, X.start, X.occ, c->ref_slot, c->ref_valid,
-        c->run_key, c->run_val, c->run_cap, &c->d_work[0], c->d_counters->v);
+    k_ref_probe<<<div_up(2 * n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(
+        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.cap,
+        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work);
     c->launches++;
   }
   CK(cudaGetLastError());
-  unsigned long long nr = 0;
-  CK(cudaMemcpyAsync(&nr, &c->d_work[0], 8, cudaMemcpyDeviceToHost, c->stream));
+  c->timings.probe_ms = t1.stop();
+  c->host_counters[CT_REF_KMERS] += R.n_windows * 2;
+
+  EvTimer t2(c->stream);
+  if (n_groups) {
+    ExpandArgs A;
+    A.rfwd = R.fwd; A.rrc = R.rc; A.rwoff = R.woff; A.rlen = R.len; A.rpbase = R.pbase; A.rgrp_read = R.grp_read;
+    A.r_npos = R.n_pos; A.ref_first_id = R.first_id;
+    A.hfwd = H.fwd; A.hwoff = H.woff; A.hlen = H.len; A.hpbase = H.pbase; A.hgrp_read = H.grp_read; A.hash_first_id = H.first_id;
+    A.K = K; A.occ = X.occ; A.ref_valid = c->ref_valid;
+    A.run_key = c->run_key; A.run_val = c->run_val; A.run_cap = c->run_cap; A.n_runs = &c->d_work[0];
+    const int grid = c->sm_count * 8;
+    k_expand_large<<<grid, 256, 0, c->stream>>>(A, c->item_large, &c->d_work[4], c->run_cap, c->d_counters->v);
+    k_expand_small<<<grid, 256, 0, c->stream>>>(A, c->item_small, &c->d_work[3], c->run_cap, c->d_counters->v);
+    c->launches += 2;
+  }
+  CK(cudaGetLastError());
+  unsigned long long w5[5] = {0, 0, 0, 0, 0};
+  CK(cudaMemcpyAsync(w5, c->d_work, 40, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->timings.expand_ms = t2.stop();
-  if (nr > c->run_cap) {
-    ovl_set_error("seed-run buffer overflow (" + std::to_string(nr) + " runs > capacity " + std::to_string(c->run_cap) + "); use a smaller ref batch");
+  const unsigned long long nr = w5[0];
+  if (w5[3] > c->run_cap || w5[4] > c->run_cap || nr > c->run_cap) {
+    ovl_set_error("seed buffer overflow (" + std::to_string(nr) + " runs, " + std::to_string(w5[3]) + "+" + std::to_string(w5[4]) +
+                  " head ranges > capacity " + std::to_string(c->run_cap) + "); use a smaller ref batch");
     c->n_runs = 0; c->n_pairs = 0;
     return OVLB_ERR_CAPACITY;
   }
   c->n_runs = nr;
   c->n_pairs = 0;
+  c->host_counters[CT_SEED_RUNS] += nr;
   c->timings.sort_ms = 0; c->timings.chain_ms = 0;
   if (nr == 0) return OVLB_OK;
 

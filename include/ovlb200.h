@@ -61,7 +61,7 @@ typedef struct ovlb_ctx ovlb_ctx;
  *  as the reference computes them (they inherit float-parsed error rates and
  *  libm results) and uploaded at create time.  */
 typedef struct {
-  uint32_t       kmer_len;              /* G.Kmer_Len, 1..31                                   */
+  uint32_t       kmer_len;              /* G.Kmer_Len, 2..30                                   */
   int32_t        partial;               /* G.Doing_Partial_Overlaps (-partial)                 */
   int32_t        unique_per_pair;       /* G.Unique_Olap_Per_Pair (-u default 1, -m 0)         */
   int32_t        min_olap_len;          /* G.Min_Olap_Len (--minlength)                        */
@@ -128,7 +128,7 @@ typedef struct {
  *  call, in milliseconds, measured with CUDA events on the context's stream.  */
 typedef struct {
   float upload_ms, encode_ms;
-  float index_count_ms, index_scan_ms, index_fill_ms, index_skip_ms;
+  float index_tuples_ms, index_sort_ms, index_table_ms, index_skip_ms;
   float probe_ms, expand_ms, sort_ms, chain_ms, extend_ms, download_ms;
   float total_ms;
 } ovlb_timings;
