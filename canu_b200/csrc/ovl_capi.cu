@@ -58,6 +58,8 @@ int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   c->mem_budget = p->device_mem_budget ? p->device_mem_budget : (uint64_t)(free_b * 0.8);
+  //  the index is probed one 32-byte sector at a time at random: do not let L2 fetch 64/128 B around each miss
+  cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaMalloc((void **)&c->d_eml, (size_t)p->n_edit_match_limit * 4));
   CK(cudaMemcpyAsync(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice, c->stream));

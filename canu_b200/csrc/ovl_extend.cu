@@ -67,7 +67,7 @@ __device__ __forceinline__ int push_at(const WarpMem &M, int i, int v_start) {
 
 //  Traceback through the from-codes, then delta encoding.  Returns delta_len; writes deltas to `out`.
 //  fwd_rules: Set_Right_Delta conventions; else Set_Left_Delta (sets leftover, may bump t_mag).
-__device__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+__device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                               int e_start, int d_start, int v_start, int row0, bool fwd_rules, int first_code,
                               int32_t *out, int &leftover, int &t_mag, int lane) {
   //  Phase A: walk down, 32 rows per round
@@ -173,7 +173,10 @@ __device__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, cons
 
 //  One banded extension (forward(), or reverse() on reverse-complemented strings).
 //  A: shorter string (m <= n), starting at base a0 of the dp4 words A; T likewise.
-__device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+//  Deliberately NOT inlined: the kernel calls it from four places (right/left extension x which read is the
+//  shorter one); one shared copy keeps the kernel's code inside the instruction cache (the fully inlined
+//  version was 17.6 k SASS instructions and spent 79 % of its stall samples waiting for instruction fetch).
+__device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                         int error_limit, bool fwd_rules, int32_t *delta_out, DpOut &o,
                         unsigned long long &cells, unsigned long long &calls, unsigned long long *err_flags, int lane) {
   o.leftover = 0; o.delta_len = 0;
@@ -195,6 +198,8 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
   uint32_t aoff = 0;
   const double bmv = P.bmv;
   int e;
+  bool reached_end = false;
+  int tb_e = 0, tb_d = 0, tb_v = 0, first_code = -1;
   __syncwarp();
 
   for (e = 1; e <= error_limit; e++) {
@@ -220,20 +225,31 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
     for (uint32_t g = 0; g < ngroups; g++) {
       const int d = Lu + (int)(g << 5) + lane;
       const bool act = d <= Ru;
-      int row = 0, code = 0;
+      int row = 0, code = 0, lim = 0, cnt = 0;
+      bool more = false;
       if (act) {
         int a = prev[(d - 1) & mask], b = prev[d & mask], c2 = prev[(d + 1) & mask];
         row = 1 + b;
         if (a > row) { row = a; code = 1; }
         if (1 + c2 > row) { row = 1 + c2; code = 2; }
-        int lim = min(m - row, n - d - row);
-        int cnt = 0;
-        while (cnt < lim) {
-          int k = ovl_match16(ovl_fetch16(A, a0 + row + cnt), ovl_fetch16(T, t0 + row + d + cnt));
-          cnt += k;
-          if (k < 16) break;
+        lim = min(m - row, n - d - row);
+        if (lim > 0) {
+          //  every lane slides its own diagonal over the first 16 bases ...
+          cnt = ovl_match16(ovl_fetch16(A, a0 + row), ovl_fetch16(T, t0 + row + d));
+          more = (cnt == 16) && (lim > 16);
+          if (cnt > lim) cnt = lim;
         }
-        row += (cnt < lim ? cnt : lim);
+      }
+      //  ... and the few diagonals that are still matching (on real overlaps: the true one) are finished by the
+      //  whole warp, 512 bases per round, instead of one lane chasing dependent loads
+      for (unsigned pend = __ballot_sync(FULL, more); pend; pend &= pend - 1) {
+        const int l = __ffs(pend) - 1;
+        const int r_l = __shfl_sync(FULL, row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, lim, l);
+        const int ext = warp_slide(A, a0 + r_l + 16, T, t0 + r_l + d_l + 16, lim_l - 16, lane);
+        if (lane == l) cnt = 16 + ext;
+      }
+      if (act) {
+        row += cnt;
         cur[d & mask] = row;
       }
       unsigned b0 = __ballot_sync(FULL, act && (code & 1));
@@ -260,14 +276,8 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
         double slope = __ddiv_rn(__dsub_rn(max_score, score), (double)tail_len);
         if (slope >= P.min_tail_slope) abort_ = true;
       }
-      if (abort_) {
-        o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
-        o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules, -1,
-                                     delta_out, o.leftover, o.t_end, lane);
-        return;
-      }
+      if (abort_) break;                                // best-so-far result, assembled after the loop
       int d = term_d;
-      int first_code = -1;
       if (fwd_rules && term_row == m && d < Ru && 1 + prev[(d + 1) & mask] == term_row) {
         //  Force the last error to be a mismatch (forward.C:215-221): the path now starts in cell (e, d+1), which
         //  the DP never evaluated (it may lie in a 32-cell group after the one that terminated), so its from-code
@@ -279,8 +289,9 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
         if (1 + pc > mx) first_code = 2;
       }
       o.a_end = term_row; o.t_end = term_row + d; o.match_to_end = 1; o.errors = e;
-      o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, e, d, term_row, row0, fwd_rules, first_code, delta_out, o.leftover, o.t_end, lane);
-      return;
+      tb_e = e; tb_d = d; tb_v = term_row;
+      reached_end = true;
+      break;
     }
     cells += (unsigned long long)width;
     aoff += ngroups;
@@ -313,10 +324,12 @@ __device__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a
     __syncwarp();
   }
 
-  //  error limit exhausted or band closed
-  o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
-  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, ms_e, ms_d, ms_e == 0 ? row0 : ms_len, row0, fwd_rules, -1,
-                               delta_out, o.leftover, o.t_end, lane);
+  if (!reached_end) {
+    //  branch point, error limit exhausted or band closed: the best-scoring prefix so far
+    o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
+    tb_e = ms_e; tb_d = ms_d; tb_v = (ms_e == 0) ? row0 : ms_len;
+  }
+  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, tb_e, tb_d, tb_v, row0, fwd_rules, first_code, delta_out, o.leftover, o.t_end, lane);
 }
 
 struct ReadView {

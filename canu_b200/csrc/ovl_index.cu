@@ -205,7 +205,8 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
   return lo;
 }
 
-__device__ __forceinline__ uint64_t slot_home(uint64_t key, uint64_t cap) { return __umul64hi(ovl_mix64(key), cap); }
+//  home slot: multiplicative (Fibonacci) hash, then scaled to [0, cap) -- every key bit reaches the top bits
+__device__ __forceinline__ uint64_t slot_home(uint64_t key, uint64_t cap) { return __umul64hi(key * 0x9E3779B97F4A7C15ull, cap); }
 
 //  find the slot of `key`, inserting it if absent; returns the slot index
 __device__ __forceinline__ uint64_t slot_find_or_insert(IndexSlot *slots, uint64_t cap, uint64_t key) {
@@ -285,13 +286,14 @@ __device__ __forceinline__ SlotView slot_lookup(const IndexSlot *__restrict__ sl
   SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
   uint64_t h = slot_home(key, cap);
   while (true) {
-    const uint4 *sp = reinterpret_cast<const uint4 *>(slots + h);
-    const uint4 a = __ldg(sp), b = __ldg(sp + 1);
-    const uint64_t k = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    //  one 256-bit load = the whole slot = one 32-byte sector (LDG.E.256 on sm_100)
+    uint64_t k, q1, q2, q3;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slots + h));
     if (k == OVL_EMPTY_KEY) return v;
     if ((k & ~OVL_SKIP_BIT) == key) {
       v.found = true; v.skip = (k & OVL_SKIP_BIT) != 0;
-      v.start = a.z; v.e0 = a.w; v.e1 = b.x; v.e2 = b.y; v.e3 = b.z; v.e4 = b.w;
+      v.start = (uint32_t)q1; v.e0 = (uint32_t)(q1 >> 32); v.e1 = (uint32_t)q2; v.e2 = (uint32_t)(q2 >> 32);
+      v.e3 = (uint32_t)q3; v.e4 = (uint32_t)(q3 >> 32);
       return v;
     }
     h = (h + 1 == cap) ? 0 : h + 1;
@@ -771,8 +773,10 @@ int ovl_build_index(ovlb_ctx *c) {
   X.n_distinct = h2[0];
   X.n_occ = h2[1];
 
-  //  one 32-byte slot per distinct k-mer (and per skip k-mer), load factor <= 0.5
-  uint64_t cap = 2 * (X.n_distinct + c->skip_keys.size()) + 64;
+  //  one 32-byte slot per distinct k-mer (and per skip k-mer); load factor 1/3 (1.25 probes per hit, 1.6 per
+  //  miss) when that fits a sixth of the memory budget, else 1/2
+  uint64_t cap = 3 * (X.n_distinct + c->skip_keys.size()) + 64;
+  if (cap * sizeof(IndexSlot) > c->mem_budget / 6) cap = 2 * (X.n_distinct + c->skip_keys.size()) + 64;
   if ((rc = ensure(X.slots, X.slots_cap, (size_t)cap, 9, 8))) return rc;
   X.cap = cap;
   CK(cudaMemsetAsync(X.slots, 0xFF, cap * sizeof(IndexSlot), c->stream));
