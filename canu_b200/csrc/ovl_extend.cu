@@ -25,7 +25,7 @@
 
 #define EXT_WARPS  8
 #define EXT_THREADS (EXT_WARPS * 32)
-#define SRING      1024                   // ints per shared ring (per row, per warp)
+#define SRING      512                    // ints per shared ring (per row, per warp)
 #define FULL       0xffffffffu
 
 struct WarpMem {
@@ -511,7 +511,7 @@ __device__ __forceinline__ void bind_warp_mem(WarpMem &M, const ExtScratch &X, i
 }
 
 //  Persistent kernel: warps pull pairs from a global cursor (pairs differ wildly in cost).
-__global__ void __launch_bounds__(EXT_THREADS)
+__global__ void __launch_bounds__(EXT_THREADS, 3)
 k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uint64_t n_pairs,
                const int32_t *__restrict__ seed_start, const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_len,
                uint8_t *seed_alive,
@@ -712,7 +712,7 @@ int ovl_prepare_ext_scratch(ovlb_ctx *c) {
   uint32_t gcap = 64; while (gcap < (uint32_t)(2 * emax + 16)) gcap <<= 1;
   X.gring_cap = gcap;
   const uint64_t per_warp = X.arena_cap * 8 + (uint64_t)gcap * 8 + (uint64_t)(emax + 2) * (4 + 4 + 1 + 4 + 4 + 4 + 4);
-  int want_warps = c->sm_count * 24;                                    // 3 CTAs of 8 warps per SM
+  int want_warps = c->sm_count * 32;                                    // up to 4 CTAs of 8 warps per SM
   uint64_t budget = c->mem_budget / 4;
   if (per_warp * want_warps > budget) want_warps = (int)(budget / per_warp);
   want_warps = (want_warps / EXT_WARPS) * EXT_WARPS;

@@ -208,10 +208,21 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
 //  home slot: multiplicative (Fibonacci) hash, then scaled to [0, cap) -- every key bit reaches the top bits
 __device__ __forceinline__ uint64_t slot_home(uint64_t key, uint64_t cap) { return __umul64hi(key * 0x9E3779B97F4A7C15ull, cap); }
 
+//  i-th slot of the probe sequence that starts at home slot h0.  A random access costs a whole 128-byte line on
+//  B200 (tools/micro/rand_sector.cu: 4 sectors of DRAM traffic per 32-byte load), so the sequence first cycles
+//  through the four slots of the home line and only then moves to the next line.  `cap` is a multiple of 4.
+__device__ __forceinline__ uint64_t probe_slot(uint64_t h0, uint32_t i, uint64_t cap) {
+  uint64_t b = (h0 >> 2) + (i >> 2);
+  const uint64_t nb = cap >> 2;
+  if (b >= nb) b -= nb;
+  return (b << 2) | ((h0 + i) & 3);
+}
+
 //  find the slot of `key`, inserting it if absent; returns the slot index
 __device__ __forceinline__ uint64_t slot_find_or_insert(IndexSlot *slots, uint64_t cap, uint64_t key) {
-  uint64_t h = slot_home(key, cap);
-  while (true) {
+  const uint64_t h0 = slot_home(key, cap);
+  for (uint32_t i = 0;; i++) {
+    const uint64_t h = probe_slot(h0, i, cap);
     unsigned long long *kp = (unsigned long long *)&slots[h].key;
     unsigned long long k = *(volatile unsigned long long *)kp;
     if ((k & ~OVL_SKIP_BIT) == key && k != OVL_EMPTY_KEY) return h;
@@ -219,7 +230,6 @@ __device__ __forceinline__ uint64_t slot_find_or_insert(IndexSlot *slots, uint64
       unsigned long long old = atomicCAS(kp, (unsigned long long)OVL_EMPTY_KEY, (unsigned long long)key);
       if (old == OVL_EMPTY_KEY || ((old & ~OVL_SKIP_BIT) == key)) return h;
     }
-    h = (h + 1 == cap) ? 0 : h + 1;
   }
 }
 
@@ -284,8 +294,9 @@ struct SlotView { bool found, skip; uint32_t start, e0, e1, e2, e3, e4; };
 
 __device__ __forceinline__ SlotView slot_lookup(const IndexSlot *__restrict__ slots, uint64_t cap, uint64_t key) {
   SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
-  uint64_t h = slot_home(key, cap);
-  while (true) {
+  const uint64_t h0 = slot_home(key, cap);
+  for (uint32_t i = 0;; i++) {
+    const uint64_t h = probe_slot(h0, i, cap);
     //  one 256-bit load = the whole slot = one 32-byte sector (LDG.E.256 on sm_100)
     uint64_t k, q1, q2, q3;
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slots + h));
@@ -296,95 +307,121 @@ __device__ __forceinline__ SlotView slot_lookup(const IndexSlot *__restrict__ sl
       v.e3 = (uint32_t)q3; v.e4 = (uint32_t)(q3 >> 32);
       return v;
     }
-    h = (h + 1 == cap) ? 0 : h + 1;
   }
 }
 
 #define SMALL_ITEM_MAX 8u
+#define STAGE_SMALL 96          // per-warp shared-memory staging of head ranges (uint4 entries)
+#define STAGE_LARGE 64
+#define PROBE_CHUNK 32          // consecutive 32-window groups handled by one warp in a row
 
-//  item = (ref position index, first occurrence, count << 1 | dir)
-__device__ __forceinline__ void emit_items(bool has, uint32_t pos, uint32_t begin, uint32_t count, int dir, int lane,
-                                           uint4 *__restrict__ small, uint4 *__restrict__ large, uint64_t item_cap,
-                                           unsigned long long *n_small, unsigned long long *n_large) {
-  const bool sm = has && count <= SMALL_ITEM_MAX, lg = has && count > SMALL_ITEM_MAX;
-  const unsigned ms = __ballot_sync(0xffffffffu, sm), ml = __ballot_sync(0xffffffffu, lg);
-  if (ms) {
-    unsigned long long base = 0;
-    const int leader = __ffs(ms) - 1;
-    if (lane == leader) base = atomicAdd(n_small, (unsigned long long)__popc(ms));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (sm) { const unsigned long long idx = base + __popc(ms & ((1u << lane) - 1)); if (idx < item_cap) small[idx] = make_uint4(pos, begin, (count << 1) | (uint32_t)dir, 0); }
-  }
-  if (ml) {
-    unsigned long long base = 0;
-    const int leader = __ffs(ml) - 1;
-    if (lane == leader) base = atomicAdd(n_large, (unsigned long long)__popc(ml));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (lg) { const unsigned long long idx = base + __popc(ml & ((1u << lane) - 1)); if (idx < item_cap) large[idx] = make_uint4(pos, begin, (count << 1) | (uint32_t)dir, 0); }
-  }
+//  Per-warp staging of items in shared memory: one global atomicAdd per ~64 items instead of one per group
+//  (13 M same-address atomics per C2 tile were the probe kernel's bottleneck).
+struct ItemStage { uint4 *buf; int n; int cap; uint4 *out; unsigned long long *counter; uint64_t out_cap; };
+
+__device__ __forceinline__ void stage_flush(ItemStage &S, int lane) {
+  if (S.n == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(S.counter, (unsigned long long)S.n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  for (int j = lane; j < S.n; j += 32)
+    if (base + j < S.out_cap) S.out[base + j] = S.buf[j];
+  __syncwarp();
+  S.n = 0;
 }
 
+//  item = (ref position index, first occurrence, count << 1 | dir)
+__device__ __forceinline__ void stage_append(ItemStage &S, bool has, uint4 item, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (!m) return;
+  if (S.n + 32 > S.cap) stage_flush(S, lane);
+  if (has) S.buf[S.n + __popc(m & ((1u << lane) - 1))] = item;
+  S.n += __popc(m);
+}
+
+//  Persistent kernel: each warp walks PROBE_CHUNK consecutive groups at a time.
 __global__ void __launch_bounds__(THREADS)
 k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, const uint64_t *__restrict__ woff,
             const uint32_t *__restrict__ len, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
             uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint64_t cap,
             uint32_t *__restrict__ ref_valid, uint32_t *rflags,
             uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work) {
-  uint64_t gg = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (gg >= 2 * n_groups) return;
+  __shared__ uint4 stage[WARPS_PER_BLOCK][STAGE_SMALL + STAGE_LARGE];
   const int lane = threadIdx.x & 31;
-  const int dir = gg >= n_groups;
-  const uint64_t g = dir ? gg - n_groups : gg;
-  const uint32_t r = grp_read[g];
-  const int L = (int)len[r];
-  const int p0 = (int)(g * 32 - pbase[r]);
-  const int p = p0 + lane;
-  const uint64_t *w = (dir ? rc : fwd) + woff[r];
+  const int wib = threadIdx.x >> 5;
+  ItemStage SS, SL;
+  SS.buf = stage[wib];               SS.n = 0; SS.cap = STAGE_SMALL; SS.out = item_small; SS.counter = &work[3]; SS.out_cap = item_cap;
+  SL.buf = stage[wib] + STAGE_SMALL; SL.n = 0; SL.cap = STAGE_LARGE; SL.out = item_large; SL.counter = &work[4]; SL.out_cap = item_cap;
 
-  uint64_t key; int cls;
-  const bool ok = warp_kmers(w, p0, L, K, lane, key, cls);
-  SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
-  if (ok) v = slot_lookup(slots, cap, key);
-  if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
-    uint32_t f = 0;
-    if (p == 0) f = 1u;
-    else {
-      if (p < OVL_HOPELESS_MATCH) f |= 1u;
-      if (L - p - K + 1 < OVL_HOPELESS_MATCH) f |= 2u;
+  const uint64_t total = 2 * n_groups;
+  const uint64_t n_chunks = (total + PROBE_CHUNK - 1) / PROBE_CHUNK;
+  for (uint64_t ch = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib; ch < n_chunks; ch += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
+    const uint64_t gg_end = min(total, (ch + 1) * PROBE_CHUNK);
+    uint32_t prev_r = 0xFFFFFFFFu; int prev_dir = -1; unsigned prev_top = 0;
+    for (uint64_t gg = ch * PROBE_CHUNK; gg < gg_end; gg++) {
+      const int dir = gg >= n_groups;
+      const uint64_t g = dir ? gg - n_groups : gg;
+      const uint32_t r = grp_read[g];
+      const int L = (int)len[r];
+      const int p0 = (int)(g * 32 - pbase[r]);
+      const int p = p0 + lane;
+      const uint64_t *w = (dir ? rc : fwd) + woff[r];
+
+      uint64_t key; int cls;
+      const bool ok = warp_kmers(w, p0, L, K, lane, key, cls);
+      SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
+      if (ok) v = slot_lookup(slots, cap, key);
+      if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
+        uint32_t f = 0;
+        if (p == 0) f = 1u;
+        else {
+          if (p < OVL_HOPELESS_MATCH) f |= 1u;
+          if (L - p - K + 1 < OVL_HOPELESS_MATCH) f |= 2u;
+        }
+        if (f) atomicOr(&rflags[2 * r + dir], f);
+      }
+      const bool valid = v.found && !v.skip && v.e4 > v.start;
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) ref_valid[((uint64_t)dir * n_pos >> 5) + g] = vm;
+      const bool carried = (r == prev_r && dir == prev_dir);    // the previous iteration was window group p0-32 of this read
+      const unsigned carry_top = prev_top;
+      prev_r = r; prev_dir = dir; prev_top = vm >> 31;
+      if (vm == 0) continue;
+
+      //  is window p-1 a hit window?  lanes 1..31 see it in the ballot; lane 0 takes it from the previous group of
+      //  this chunk, or (first group of a chunk) looks window p0-1 up itself
+      bool prev_valid = (lane > 0) ? ((vm >> (lane - 1)) & 1u) : (carried && carry_top);
+      if (lane == 0 && !carried && valid && p0 > 0 && cls != 0) {
+        //  k-mer of window p0-1 = my k-mer shifted up one base with ref[p0-1] in front (it cannot contain an N:
+        //  its last K-1 bases are mine and cls != 0 says base p0-1 is ACGT)
+        const uint64_t pk = ((key << 2) | (uint64_t)(cls - 1)) & ((1ull << (2 * K)) - 1);
+        const SlotView pv = slot_lookup(slots, cap, pk);
+        prev_valid = pv.found && !pv.skip && pv.e4 > pv.start;
+      }
+
+      //  head ranges: the whole list, or the list minus the class of ref[p-1]
+      uint32_t b0 = v.start, n0 = 0, b1 = 0, n1 = 0;
+      if (valid) {
+        if (prev_valid && cls != 0) {
+          const uint32_t lo = (cls == 1) ? v.e0 : (cls == 2) ? v.e1 : (cls == 3) ? v.e2 : v.e3;     // start of class cls
+          const uint32_t hi = (cls == 1) ? v.e1 : (cls == 2) ? v.e2 : (cls == 3) ? v.e3 : v.e4;     // end of class cls
+          n0 = lo - v.start; b1 = hi; n1 = v.e4 - hi;
+        } else {
+          n0 = v.e4 - v.start;
+        }
+      }
+      if (__any_sync(0xffffffffu, n0 | n1)) {
+        const uint32_t pos = (uint32_t)(g * 32 + lane);
+        stage_append(SS, n0 > 0 && n0 <= SMALL_ITEM_MAX, make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
+        stage_append(SL, n0 > SMALL_ITEM_MAX,            make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
+        stage_append(SS, n1 > 0 && n1 <= SMALL_ITEM_MAX, make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+        stage_append(SL, n1 > SMALL_ITEM_MAX,            make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+      }
     }
-    if (f) atomicOr(&rflags[2 * r + dir], f);
   }
-  const bool valid = v.found && !v.skip && v.e4 > v.start;
-  const unsigned vm = __ballot_sync(0xffffffffu, valid);
-  if (lane == 0) ref_valid[((uint64_t)dir * n_pos >> 5) + g] = vm;
-  if (vm == 0) return;
-
-  //  is window p-1 a hit window?  lanes 1..31 see it in the ballot; lane 0 looks window p0-1 up itself
-  bool prev_valid = (lane > 0) && ((vm >> (lane - 1)) & 1u);
-  if (lane == 0 && valid && p0 > 0 && cls != 0) {
-    //  k-mer of window p0-1 = my k-mer shifted up one base with ref[p0-1] in front (it cannot contain an N:
-    //  its last K-1 bases are mine and cls != 0 says base p0-1 is ACGT)
-    const uint64_t pk = ((key << 2) | (uint64_t)(cls - 1)) & ((1ull << (2 * K)) - 1);
-    const SlotView pv = slot_lookup(slots, cap, pk);
-    prev_valid = pv.found && !pv.skip && pv.e4 > pv.start;
-  }
-
-  //  head ranges: the whole list, or the list minus the class of ref[p-1]
-  uint32_t b0 = v.start, n0 = 0, b1 = 0, n1 = 0;
-  if (valid) {
-    if (prev_valid && cls != 0) {
-      const uint32_t lo = (cls == 1) ? v.e0 : (cls == 2) ? v.e1 : (cls == 3) ? v.e2 : v.e3;     // start of class cls
-      const uint32_t hi = (cls == 1) ? v.e1 : (cls == 2) ? v.e2 : (cls == 3) ? v.e3 : v.e4;     // end of class cls
-      n0 = lo - v.start; b1 = hi; n1 = v.e4 - hi;
-    } else {
-      n0 = v.e4 - v.start;
-    }
-  }
-  const uint32_t pos = (uint32_t)(g * 32 + lane);
-  if (__any_sync(0xffffffffu, n0 | n1)) {
-    emit_items(n0 > 0, pos, b0, n0, dir, lane, item_small, item_large, item_cap, &work[3], &work[4]);
-    emit_items(n1 > 0, pos, b1, n1, dir, lane, item_small, item_large, item_cap, &work[3], &work[4]);
-  }
+  stage_flush(SS, lane);
+  stage_flush(SL, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,6 +814,7 @@ int ovl_build_index(ovlb_ctx *c) {
   //  miss) when that fits a sixth of the memory budget, else 1/2
   uint64_t cap = 3 * (X.n_distinct + c->skip_keys.size()) + 64;
   if (cap * sizeof(IndexSlot) > c->mem_budget / 6) cap = 2 * (X.n_distinct + c->skip_keys.size()) + 64;
+  cap = (cap + 3) & ~3ull;                              // whole 128-byte lines of four slots
   if ((rc = ensure(X.slots, X.slots_cap, (size_t)cap, 9, 8))) return rc;
   X.cap = cap;
   CK(cudaMemsetAsync(X.slots, 0xFF, cap * sizeof(IndexSlot), c->stream));
@@ -840,7 +878,10 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
 
   EvTimer t1(c->stream);
   if (n_groups) {
-    k_ref_probe<<<div_up(2 * n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(
+    int per_sm = 4;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ref_probe, THREADS, 0);
+    if (per_sm < 1) per_sm = 1;
+    k_ref_probe<<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
         R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.cap,
         c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work);
     c->launches++;
