@@ -55,6 +55,11 @@ class _Counters(C.Structure):
         "ref_kmers", "seed_hits", "seed_runs", "pairs")]
 
 
+class _Tile(C.Structure):
+    _fields_ = [("hash_bgn", C.c_uint32), ("hash_end", C.c_uint32), ("ref_bgn", C.c_uint32), ("ref_end", C.c_uint32),
+                ("hash_bases", C.c_uint64), ("ref_bases", C.c_uint64), ("cost", C.c_double), ("has_hash_reads", C.c_int32)]
+
+
 class _Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "upload_ms", "encode_ms", "index_tuples_ms", "index_sort_ms", "index_table_ms", "index_skip_ms",
@@ -73,7 +78,7 @@ EXPORTS = [
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_debug_pairs", "ovlb_debug_extend",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
-    "ovlb_reads_free", "ovlb_kmer_keys",
+    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_assign_tiles",
 ]
 
 
@@ -118,6 +123,9 @@ def load_library():
     L.ovlb_reads_view.restype = C.POINTER(_Reads)
     L.ovlb_reads_free.argtypes = [C.c_void_p]
     L.ovlb_kmer_keys.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.ovlb_plan_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                  C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ovlb_assign_tiles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     _LIB = L
     return L
 
@@ -310,6 +318,38 @@ class Overlapper:
         _check(self.L.ovlb_debug_extend(self._h, n, *[x.ctypes.data for x in a], out.ctypes.data,
                                         deltas.ctypes.data if delta_stride else None, delta_stride))
         return out, deltas
+
+
+def plan_tiles(read_lens, min_olap_len, hash_block_len, ref_block_len, hash_range=None, ref_range=None,
+               strict_reference=False):
+    """Cut a read set into hash-block x ref-block tiles like overlapInCorePartition
+    (overlapInCorePartition.C:127-257).  read_lens[i] is the length of read ID i+1.
+    Returns a list of dicts (hash_bgn, hash_end, ref_bgn, ref_end, hash_bases, ref_bases, cost)."""
+    L = load_library()
+    n = len(read_lens)
+    rl = np.zeros(n + 2, dtype=np.uint32)
+    rl[1:n + 1] = np.asarray(read_lens, dtype=np.uint32)
+    hb, he = hash_range if hash_range else (1, n)
+    rb, re_ = ref_range if ref_range else (1, n)
+    cnt = C.c_uint64()
+    _check(L.ovlb_plan_tiles(rl.ctypes.data, n, min_olap_len, hash_block_len, ref_block_len, hb, he, rb, re_,
+                             int(strict_reference), None, 0, C.byref(cnt)))
+    arr = (_Tile * max(cnt.value, 1))()
+    _check(L.ovlb_plan_tiles(rl.ctypes.data, n, min_olap_len, hash_block_len, ref_block_len, hb, he, rb, re_,
+                             int(strict_reference), C.cast(arr, C.c_void_p), cnt.value, C.byref(cnt)))
+    return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
+
+
+def assign_tiles(tiles, n_workers):
+    """Longest-processing-time-first owner of every tile (deterministic); returns a list of worker indices."""
+    L = load_library()
+    arr = (_Tile * max(len(tiles), 1))()
+    for i, t in enumerate(tiles):
+        for f, _ in _Tile._fields_:
+            setattr(arr[i], f, t[f])
+    owner = np.zeros(max(len(tiles), 1), dtype=np.uint32)
+    _check(L.ovlb_assign_tiles(C.cast(arr, C.c_void_p), len(tiles), n_workers, owner.ctypes.data))
+    return owner[:len(tiles)].tolist()
 
 
 def stats_lines(c: dict) -> str:

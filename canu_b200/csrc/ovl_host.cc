@@ -6,6 +6,7 @@
 //  reference's operation order (and without FMA contraction: compiled with -ffp-contract=off).
 #include "../../include/ovlb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -181,6 +182,88 @@ int ovlb_kmer_keys(const char *kmer, uint32_t kmer_len, uint64_t *fwd_key, uint6
     r |= (3 - code) << (2 * (kmer_len - 1 - j));
   }
   *fwd_key = f; *rc_key = r;
+  return OVLB_OK;
+}
+
+//  overlapInCorePartition's partitionLength() (overlapInCorePartition.C:127-257), default library case
+//  (no -H/-R restriction): hash blocks of at least hash_block_len bytes (one per base plus one per read),
+//  each crossed with ref blocks of at least ref_block_len bases; a ref block never extends past the last
+//  read of its hash block, because only refID < hashID pairs are computed.
+//
+//  strict_reference = 1 reproduces the reference loop bounds exactly (its `while (hashBeg < hashMax)` /
+//  `while (refBeg < refMax)` never start a block on the last read); 0 covers every read.
+int ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
+                    uint64_t hash_block_len, uint64_t ref_block_len,
+                    uint32_t hash_min, uint32_t hash_max, uint32_t ref_min, uint32_t ref_max,
+                    int strict_reference, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out) {
+  if (!read_len || !n_out) { ovl_set_error("ovlb_plan_tiles: null argument"); return OVLB_ERR_ARG; }
+  if (hash_block_len == 0 || ref_block_len == 0) { ovl_set_error("ovlb_plan_tiles: block lengths must be positive"); return OVLB_ERR_ARG; }
+  if (hash_min < 1) hash_min = 1;
+  if (ref_min < 1) ref_min = 1;
+  if (hash_max > n_reads) hash_max = n_reads;
+  if (ref_max > n_reads) ref_max = n_reads;
+  const uint32_t lastStartAdj = strict_reference ? 0 : 1;       // reference: strictly below the max; ours: up to it
+  uint64_t totalHashable = 0;
+  for (uint32_t id = hash_min; id <= hash_max; id++) if (read_len[id] >= min_olap_len) totalHashable += (uint64_t)read_len[id] + 1;
+  uint64_t n = 0;
+  uint32_t hashBeg = hash_min, hashEnd = hash_min - 1;
+  while (hashBeg < hash_max + lastStartAdj) {
+    uint64_t hashLen = 0, hashBases = 0; uint32_t hashReads = 0;
+    do {
+      hashEnd++;
+      if (read_len[hashEnd] < min_olap_len) continue;
+      hashLen += (uint64_t)read_len[hashEnd] + 1;
+      hashReads += 1;
+      hashBases += (uint64_t)read_len[hashEnd] + 1;
+    } while (hashLen < hash_block_len && hashEnd < hash_max);
+
+    uint32_t refBeg = ref_min, refEnd = 0;
+    if (!strict_reference) refEnd = ref_min - 1;
+    while (refBeg < ref_max + lastStartAdj && refBeg < hashEnd) {
+      uint64_t refLen = 0, refBases = 0;
+      do {
+        refEnd++;
+        if (read_len[refEnd] < min_olap_len) continue;
+        refLen += read_len[refEnd];
+        refBases += (uint64_t)read_len[refEnd] + 1;
+      } while (refLen < ref_block_len && refEnd < ref_max);
+      if (refEnd > ref_max) refEnd = ref_max;
+      if (refEnd > hashEnd) refEnd = hashEnd;
+      if (out && n < out_cap) {
+        ovlb_tile &t = out[n];
+        t.hash_bgn = hashBeg; t.hash_end = hashEnd; t.ref_bgn = refBeg; t.ref_end = refEnd;
+        uint64_t rb = 0;                                 // ref bases actually inside the (clamped) block
+        for (uint32_t id = refBeg; id <= refEnd; id++) if (read_len[id] >= min_olap_len) rb += read_len[id];
+        t.hash_bases = hashBases; t.ref_bases = rb;
+        //  cost model: index build ~ hash bases; lookup ~ 2 orientations of the ref bases; extension ~ ref bases
+        //  x the share of all hashable reads that sit in this hash block (= share of each read's overlaps found here)
+        t.cost = (double)hashBases + (double)rb * (2.0 + 8.0 * (double)hashBases / (double)(totalHashable ? totalHashable : 1));
+        t.has_hash_reads = hashReads != 0;
+      }
+      n++;
+      refBeg = refEnd + 1;
+    }
+    hashBeg = hashEnd + 1;
+  }
+  *n_out = n;
+  if (out && n > out_cap) { ovl_set_error("ovlb_plan_tiles: output buffer too small"); return OVLB_ERR_CAPACITY; }
+  return OVLB_OK;
+}
+
+//  Longest-processing-time-first assignment of tiles to workers: tiles sorted by cost
+//  descending, each given to the currently least-loaded worker.  Deterministic (ties: lower index first).
+int ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner) {
+  if ((n_tiles && (!tiles || !owner)) || n_workers == 0) { ovl_set_error("ovlb_assign_tiles: bad argument"); return OVLB_ERR_ARG; }
+  std::vector<uint64_t> order(n_tiles);
+  for (uint64_t i = 0; i < n_tiles; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return tiles[a].cost > tiles[b].cost; });
+  std::vector<double> load(n_workers, 0.0);
+  for (uint64_t k = 0; k < n_tiles; k++) {
+    uint32_t best = 0;
+    for (uint32_t w = 1; w < n_workers; w++) if (load[w] < load[best]) best = w;
+    owner[order[k]] = best;
+    load[best] += tiles[order[k]].cost;
+  }
   return OVLB_OK;
 }
 

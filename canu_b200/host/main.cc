@@ -7,14 +7,16 @@
 //
 //  Flags that only size the reference's CPU data structures are accepted and ignored because the
 //  output does not depend on them: --hashbits, --hashload, --hashdatalen, -t.
-//  Extra flags of this build: --gpu N (device, default 0), --refbatch BASES, --hashblock BASES.
+//  Extra flags of this build: --gpu N (device, default 0), --gpus a,b,..|all, --refbatch BASES, --hashblock BASES.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include <sys/stat.h>
 
@@ -36,6 +38,7 @@ struct Options {
   bool     minKmers = false, noHopeless = false;
   double   maxErate = 0.06, alignNoise = 1.0;
   int      gpu = 0;
+  std::vector<int> gpus;           // --gpus a,b,..  (or "all")
   uint64_t refBatchBases = 0, hashBlockBases = 0;
 };
 
@@ -70,6 +73,7 @@ static void usage(const char *argv0) {
   fprintf(stderr, "--minkmers         filter candidate pairs by k-mer count\n\n");
   fprintf(stderr, "--hashbits n / --hashdatalen n / --hashload f   accepted and ignored (output does not depend on them)\n\n");
   fprintf(stderr, "--gpu n            CUDA device to use (default 0)\n");
+  fprintf(stderr, "--gpus a,b,..|all  spread the job's hash-block x ref-block tiles over several CUDA devices\n");
   fprintf(stderr, "--refbatch n       bases of reference reads per device batch\n");
   fprintf(stderr, "--hashblock n      bases of hash reads per device-resident index\n\n");
 }
@@ -178,6 +182,12 @@ int main(int argc, char **argv) {
     else if (!strcmp(a, "--alignnoise"))  G.alignNoise = ovlb_parse_erate(need(a));
     else if (!strcmp(a, "-z"))            G.noHopeless = true;
     else if (!strcmp(a, "--gpu"))         G.gpu = atoi(need(a));
+    else if (!strcmp(a, "--gpus")) {
+      const char *v = need(a);
+      G.gpus.clear();
+      if (!strcmp(v, "all")) G.gpus.push_back(-1);
+      else for (const char *q = v; *q; ) { G.gpus.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
+    }
     else if (!strcmp(a, "--refbatch"))    G.refBatchBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--hashblock"))   G.hashBlockBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--version"))     { printf("overlapInCore (canu_b200, B200-native ovl) for canu v2.3\n"); return 0; }
@@ -200,17 +210,27 @@ int main(int argc, char **argv) {
   if (G.bgnRefID < 1)  G.bgnRefID = 1;
   if (G.endRefID > N)  G.endRefID = N;
 
+  const int ndev = ovlb_device_count();
+  if (ndev == 0) FAIL("ERROR: no CUDA device found; this overlapInCore has no CPU path.");
+  if (G.gpus.empty()) G.gpus.push_back(G.gpu);
+  if (G.gpus.size() == 1 && G.gpus[0] < 0) { G.gpus.clear(); for (int d = 0; d < ndev; d++) G.gpus.push_back(d); }
+  for (int d : G.gpus) if (d < 0 || d >= ndev) FAIL("ERROR: --gpu/--gpus names device %d but only %d CUDA device(s) exist", d, ndev);
+  const uint32_t W = (uint32_t)G.gpus.size();
+
+  //  A read must be at least --minlength long to be hashed or searched, and at least K long to hold a k-mer.
+  const uint32_t minLen = (uint32_t)std::max<int64_t>(G.minOlapLen, (int64_t)G.kmerLen);
   uint32_t maxLen = 64;
-  for (uint32_t id = std::min(G.bgnHashID, G.bgnRefID); id <= std::max(G.endHashID, G.endRefID) && id <= N; id++)
-    maxLen = std::max(maxLen, store.readLength(id));
+  std::vector<uint32_t> readLen(N + 2, 0);
+  uint64_t refBasesTotal = 0;
+  for (uint32_t id = 1; id <= N; id++) {
+    readLen[id] = store.readLength(id);
+    if (id >= std::min(G.bgnHashID, G.bgnRefID) && id <= std::max(G.endHashID, G.endRefID)) maxLen = std::max(maxLen, readLen[id]);
+    if (id >= G.bgnRefID && id <= G.endRefID && readLen[id] >= minLen) refBasesTotal += readLen[id];
+  }
 
   ovlb_params P;
   if (ovlb_params_init(&P, (uint32_t)G.kmerLen, G.maxErate, G.alignNoise, G.partial, G.unique, G.minOlapLen, G.noHopeless, G.minKmers, maxLen))
     FAIL("ERROR: %s", ovlb_last_error());
-
-  if (ovlb_device_count() == 0) FAIL("ERROR: no CUDA device found; this overlapInCore has no CPU path.");
-  ovlb_ctx *ctx = nullptr;
-  if (ovlb_create(G.gpu, &P, &ctx)) FAIL("ERROR: %s", ovlb_last_error());
 
   std::vector<uint64_t> skip;
   if (G.kmerSkipFileName && load_skip_kmers(G.kmerSkipFileName, (uint32_t)G.kmerLen, skip)) return 1;
@@ -218,68 +238,114 @@ int main(int argc, char **argv) {
   OvFileWriter out;
   if (!out.open(G.outName, N, e)) FAIL("ERROR: %s", e.c_str());
 
-  //  A read must be at least --minlength long to be hashed or searched, and at least K long to hold a k-mer.
-  const uint32_t minLen = (uint32_t)std::max<int64_t>(G.minOlapLen, (int64_t)G.kmerLen);
-  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : 1500000000ull;   // index footprint ~45 B/base
+  //  Re-block the job inside the process (the output does not depend on blocking): hash blocks
+  //  sized for HBM, ref batches sized for the device seed buffers -- and small enough that every GPU gets several.
+  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : 1500000000ull;
   uint64_t refBatch = G.refBatchBases ? G.refBatchBases : 256000000ull;
+  if (W > 1 && !G.refBatchBases) refBatch = std::max<uint64_t>(std::min<uint64_t>(refBatch, refBasesTotal / (4ull * W) + 1), 4000000ull);
 
-  fprintf(stderr, "overlapInCore (B200): store '%s' has %u reads (version flags 0x%x); hash %u-%u ref %u-%u\n",
-          G.storePath, N, store.version(), G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID);
-
-  Packed HB, RB;
-  std::vector<ovlb_record> recs;
-  uint32_t hb = G.bgnHashID;
-  while (hb <= G.endHashID && G.bgnHashID <= G.endHashID) {
-    //  choose the hash block [hb, he] by bases
-    uint32_t he = hb; uint64_t bases = 0;
-    while (he <= G.endHashID) {
-      uint32_t L = store.readLength(he);
-      if (bases > 0 && bases + L > hashBlock) break;
-      bases += L; he++;
+  std::vector<ovlb_tile> tiles;
+  {
+    uint64_t nt = 0;
+    //  blocks are cut on read lengths with --minlength 0 so that short reads still belong to some block
+    if (G.bgnHashID <= G.endHashID && G.bgnRefID <= G.endRefID) {
+      if (ovlb_plan_tiles(readLen.data(), N, 0, hashBlock, refBatch, G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID, 0, nullptr, 0, &nt))
+        FAIL("ERROR: %s", ovlb_last_error());
+      tiles.resize(nt);
+      if (nt && ovlb_plan_tiles(readLen.data(), N, 0, hashBlock, refBatch, G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID, 0, tiles.data(), nt, &nt))
+        FAIL("ERROR: %s", ovlb_last_error());
     }
-    he--;
-    if (!pack_range(store, hb, he, G.minLibToHash, G.maxLibToHash, minLen, HB, e)) FAIL("ERROR: %s", e.c_str());
-    fprintf(stderr, "Build_Hash_Index from %u to %u (%lu bases)\n", hb, he, (unsigned long)HB.bases);
-    if (ovlb_load_hash_reads(ctx, &HB.view)) FAIL("ERROR: %s", ovlb_last_error());
-    if (!skip.empty() && ovlb_mark_skip_kmers(ctx, skip.data(), skip.size())) FAIL("ERROR: %s", ovlb_last_error());
-    if (ovlb_build_index(ctx)) FAIL("ERROR: %s", ovlb_last_error());
-
-    //  only ref reads with ID below the last hash read can produce pairs (refID < hashID)
-    const uint32_t re = std::min(G.endRefID, he > 0 ? he - 1 : 0);
-    uint32_t rb = G.bgnRefID;
-    while (rb <= re) {
-      uint32_t r2 = rb; uint64_t rbases = 0;
-      while (r2 <= re && r2 - rb < 200000) {
-        uint32_t L = store.readLength(r2);
-        if (rbases > 0 && rbases + L > refBatch) break;
-        rbases += L; r2++;
-      }
-      r2--;
-      if (!pack_range(store, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RB, e)) FAIL("ERROR: %s", e.c_str());
-      uint64_t n = 0;
-      int rc = ovlb_stage_ref_batch(ctx, &RB.view);
-      if (!rc) rc = ovlb_run_staged(ctx, &n);
-      if (rc == OVLB_ERR_CAPACITY && r2 > rb) {                       // seed buffers overflowed: halve the batch
-        refBatch = std::max<uint64_t>(rbases / 2, 1000000);
-        fprintf(stderr, "ref batch %u-%u too large for the device buffers (%s); retrying with %lu bases per batch\n",
-                rb, r2, ovlb_last_error(), (unsigned long)refBatch);
-        continue;
-      }
-      if (rc) FAIL("ERROR: %s", ovlb_last_error());
-      recs.resize(n);
-      if (ovlb_fetch_records(ctx, recs.data(), recs.size(), &n)) FAIL("ERROR: %s", ovlb_last_error());
-      fprintf(stderr, "Processed reads %u-%u (%lu bases): %lu overlaps\n", rb, r2, (unsigned long)rbases, (unsigned long)n);
-      out.submit(std::move(recs));
-      recs = std::vector<ovlb_record>();
-      rb = r2 + 1;
+  }
+  //  owner of every tile: whole hash blocks per GPU when there are plenty of them (no index is built twice),
+  //  else tile by tile (the hash block is then indexed on every GPU that got one of its tiles)
+  std::vector<uint32_t> owner(tiles.size(), 0);
+  if (W > 1 && !tiles.empty()) {
+    std::vector<ovlb_tile> blocks;                                     // one pseudo-tile per hash block, cost summed
+    std::vector<size_t> blockOf(tiles.size());
+    for (size_t i = 0; i < tiles.size(); i++) {
+      if (blocks.empty() || blocks.back().hash_bgn != tiles[i].hash_bgn) { blocks.push_back(tiles[i]); blocks.back().cost = 0; }
+      blocks.back().cost += tiles[i].cost;
+      blockOf[i] = blocks.size() - 1;
     }
-    hb = he + 1;
+    if (blocks.size() >= 2 * (size_t)W) {
+      std::vector<uint32_t> bo(blocks.size());
+      if (ovlb_assign_tiles(blocks.data(), blocks.size(), W, bo.data())) FAIL("ERROR: %s", ovlb_last_error());
+      for (size_t i = 0; i < tiles.size(); i++) owner[i] = bo[blockOf[i]];
+    } else if (ovlb_assign_tiles(tiles.data(), tiles.size(), W, owner.data())) FAIL("ERROR: %s", ovlb_last_error());
   }
 
+  fprintf(stderr, "overlapInCore (B200): store '%s' has %u reads (version flags 0x%x); hash %u-%u ref %u-%u; %zu tile(s) on %u GPU(s)\n",
+          G.storePath, N, store.version(), G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID, tiles.size(), W);
+
+  //  One worker thread per GPU; tiles share nothing, records go to the one writer thread, counters are summed.
+  std::vector<ovlb_counters> counters(W);
+  std::vector<std::string> werr(W);
+  std::mutex log_mu;
+  auto worker = [&](uint32_t wi) {
+    memset(&counters[wi], 0, sizeof(ovlb_counters));
+    std::string err;
+    SqStore st;                                                         // the reader is stateful: one per thread
+    if (!st.open(G.storePath, err)) { werr[wi] = err; return; }
+    ovlb_ctx *ctx = nullptr;
+    if (ovlb_create(G.gpus[wi], &P, &ctx)) { werr[wi] = ovlb_last_error(); return; }
+    Packed HB, RB;
+    uint32_t curHb = 0, curHe = 0;
+    std::vector<ovlb_record> recs;
+    std::vector<std::pair<uint32_t, uint32_t>> todo;                    // ref ranges of the current tile (split on overflow)
+    for (size_t ti = 0; ti < tiles.size() && werr[wi].empty(); ti++) {
+      if (owner[ti] != wi) continue;
+      const ovlb_tile &T = tiles[ti];
+      if (T.hash_bgn != curHb || T.hash_end != curHe) {
+        if (!pack_range(st, T.hash_bgn, T.hash_end, G.minLibToHash, G.maxLibToHash, minLen, HB, err)) { werr[wi] = err; break; }
+        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Build_Hash_Index from %u to %u (%lu bases)\n", G.gpus[wi], T.hash_bgn, T.hash_end, (unsigned long)HB.bases); }
+        if (ovlb_load_hash_reads(ctx, &HB.view) ||
+            (!skip.empty() && ovlb_mark_skip_kmers(ctx, skip.data(), skip.size())) ||
+            ovlb_build_index(ctx)) { werr[wi] = ovlb_last_error(); break; }
+        curHb = T.hash_bgn; curHe = T.hash_end;
+      }
+      //  only ref reads with ID below the last hash read can produce pairs (refID < hashID)
+      const uint32_t re = std::min(T.ref_end, T.hash_end > 0 ? T.hash_end - 1 : 0);
+      todo.clear();
+      if (T.ref_bgn <= re) todo.push_back({T.ref_bgn, re});
+      while (!todo.empty() && werr[wi].empty()) {
+        const uint32_t rb = todo.back().first, r2 = todo.back().second;
+        todo.pop_back();
+        if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RB, err)) { werr[wi] = err; break; }
+        uint64_t n = 0;
+        int rc = (r2 - rb + 1 > 200000) ? OVLB_ERR_CAPACITY : ovlb_stage_ref_batch(ctx, &RB.view);
+        if (!rc) rc = ovlb_run_staged(ctx, &n);
+        if (rc == OVLB_ERR_CAPACITY && r2 > rb) {                       // seed buffers overflowed: halve the batch
+          const uint32_t mid = rb + (r2 - rb) / 2;
+          todo.push_back({mid + 1, r2}); todo.push_back({rb, mid});
+          continue;
+        }
+        if (rc) { werr[wi] = ovlb_last_error(); break; }
+        recs.resize(n);
+        if (ovlb_fetch_records(ctx, recs.data(), recs.size(), &n)) { werr[wi] = ovlb_last_error(); break; }
+        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", G.gpus[wi], rb, r2, T.hash_bgn, T.hash_end, (unsigned long)RB.bases, (unsigned long)n); }
+        out.submit(std::move(recs));
+        recs = std::vector<ovlb_record>();
+      }
+    }
+    if (werr[wi].empty() && ovlb_get_counters(ctx, &counters[wi])) werr[wi] = ovlb_last_error();
+    ovlb_destroy(ctx);
+  };
+  if (W == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t wi = 0; wi < W; wi++) th.emplace_back(worker, wi);
+    for (auto &t : th) t.join();
+  }
+  for (uint32_t wi = 0; wi < W; wi++) if (!werr[wi].empty()) FAIL("ERROR: [gpu %d] %s", G.gpus[wi], werr[wi].c_str());
+
   ovlb_counters C;
-  if (ovlb_get_counters(ctx, &C)) FAIL("ERROR: %s", ovlb_last_error());
+  memset(&C, 0, sizeof(C));
+  for (uint32_t wi = 0; wi < W; wi++) {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(&counters[wi]);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(&C);
+    for (size_t k = 0; k < sizeof(ovlb_counters) / 8; k++) dst[k] += src[k];
+  }
   if (!out.close(e)) FAIL("ERROR: %s", e.c_str());
-  ovlb_destroy(ctx);
   ovlb_params_free(&P);
 
   FILE *stats = stderr;

@@ -224,6 +224,30 @@ void   ovlb_reads_free(ovlb_reads_owner *o);
 /*  k-mer text -> key (base j in bits 2j..2j+1); returns 0 on success, fills fwd and reverse-complement keys. */
 int    ovlb_kmer_keys(const char *kmer, uint32_t kmer_len, uint64_t *fwd_key, uint64_t *rc_key);
 
+/* ---------------------------------------------------------------------------------------------
+ *  Tile planning for multi-GPU runs (host only).  Replaces overlapInCorePartition's partitionLength()
+ *  (overlapInCorePartition.C:127-257): the read range is cut into hash blocks x ref blocks; every tile is
+ *  one `overlapInCore -h hash_bgn-hash_end -r ref_bgn-ref_end --hashdatalen hash_bases` job and tiles share
+ *  nothing, so they are spread over GPUs without any collective.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t hash_bgn, hash_end, ref_bgn, ref_end;   /* inclusive read ID ranges                        */
+  uint64_t hash_bases;                             /* the --hashdatalen value: bases + reads hashed   */
+  uint64_t ref_bases;
+  double   cost;                                   /* relative cost estimate used for load balancing  */
+  int32_t  has_hash_reads;                         /* reference omits --hashdatalen when 0            */
+} ovlb_tile;
+
+/*  read_len[id] for id in 1..n_reads (read_len[0] unused).  With out == NULL only counts.
+ *  strict_reference = 1: reproduce the reference's loop bounds (the last read never starts a block);
+ *  0: cover every read.  */
+int  ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
+                     uint64_t hash_block_len, uint64_t ref_block_len,
+                     uint32_t hash_min, uint32_t hash_max, uint32_t ref_min, uint32_t ref_max,
+                     int strict_reference, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
+/*  owner[i] in [0, n_workers): longest-processing-time-first on tiles[i].cost, deterministic.  */
+int  ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,34 @@ def test_drop_in_executable_on_sqstore(case, tmp_path):
     assert got == want, _diff_msg(got, want)
     assert open(str(tmp_path / "out.stats")).read() == open(os.path.join(gu.GOLDEN, case + ".stats")).read()
     assert open(str(tmp_path / "out.oc"), "rb").read() == open(os.path.join(gu.GOLDEN, case + ".oc"), "rb").read()
+
+
+@pytest.mark.parametrize("extra", [["--gpus", "0,0", "--hashblock", "250000", "--refbatch", "120000"],
+                                   ["--gpus", "0,0,0", "--hashblock", "60000", "--refbatch", "400000"],
+                                   ["--gpus", "all"]])
+def test_drop_in_executable_multi_worker(extra, tmp_path):
+    """The multi-GPU path of the host driver (tile plan -> LPT owners -> one worker thread and context per
+    device -> one writer): with a device listed several times the same code runs on a one-GPU box.  Output must
+    be the golden single-tile output whatever the tiling."""
+    import os
+    import subprocess
+    _api()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "canu_b200", "bin", "overlapInCore")
+    tool = os.path.join(root, "canu_b200", "bin", "ovltool")
+    c = gu.get_case("A_default")
+    store = os.path.join(gu.GOLDEN, "A.seqStore")
+    ovb = str(tmp_path / "out.ovb")
+    cmd = [exe, "-t", "4", "-k", "22", "--hashbits", "22", "--hashload", "0.8", "--minlength", "500"] + c["flags"] + extra + [
+        "-h", "1-220", "-r", "1-220", "-o", ovb, "-s", str(tmp_path / "out.stats"), store]
+    r = subprocess.run(cmd, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines = subprocess.check_output([tool, "dump-ovb", ovb]).decode().splitlines()
+    recs = np.zeros(len(lines), dtype=[("a_iid", "<u4"), ("b_iid", "<u4"), ("w0", "<u8"), ("w1", "<u8")])
+    for i, ln in enumerate(lines):
+        x = ln.split()
+        recs[i] = (int(x[0]), int(x[1]), int(x[2], 16), int(x[3], 16))
+    got, want = gu.format_records(recs), gu.load_golden_lines("A_default")
+    assert got == want, _diff_msg(got, want)
+    assert open(str(tmp_path / "out.stats")).read() == open(os.path.join(gu.GOLDEN, "A_default.stats")).read()
+    assert open(str(tmp_path / "out.oc"), "rb").read() == open(os.path.join(gu.GOLDEN, "A_default.oc"), "rb").read()

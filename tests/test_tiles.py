@@ -1,0 +1,81 @@
+"""Tile planning: the planner behind the multi-GPU runs must cut the job grid exactly like
+the reference's overlapInCorePartition, and the tiles, spread over ranks, must reproduce the single-tile result.
+CPU only: the planner is host code of the C ABI; the per-tile overlaps here come from the ORACLE (the checker),
+which lets the N>1 sharding logic be tested with world_size 2 on `gloo` without a GPU."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lens(store):
+    return [len(r) for r in gu.load_dump_reads(store)]
+
+
+def _opt_line(t):
+    s = "-h %d-%d -r %d-%d" % (t["hash_bgn"], t["hash_end"], t["ref_bgn"], t["ref_end"])
+    if t["has_hash_reads"]:
+        s += " --hashdatalen %d" % t["hash_bases"]
+    return s
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(gu.GOLDEN, "partition.json"))),
+                         ids=lambda c: "%s-hl%d-rl%d-ol%d" % (c["store"], c["hl"], c["rl"], c["ol"]))
+def test_plan_matches_reference_partition(case):
+    """Bit-exact against the .ovlopt lines the reference overlapInCorePartition wrote for the same store."""
+    from canu_b200 import api
+    tiles = api.plan_tiles(_lens(case["store"]), case["ol"], case["hl"], case["rl"], strict_reference=True)
+    assert [_opt_line(t) for t in tiles] == case["ovlopt"]
+
+
+@pytest.mark.parametrize("hl,rl", [(200000, 400000), (60000, 90000), (10 ** 9, 10 ** 9), (1, 1)])
+def test_full_cover_plan_covers_every_pair_once(hl, rl):
+    """strict_reference=False: every (ref < hash) read pair lies in exactly one tile."""
+    from canu_b200 import api
+    lens = _lens("A")
+    n = len(lens)
+    tiles = api.plan_tiles(lens, 500, hl, rl, strict_reference=False)
+    cover = np.zeros((n + 1, n + 1), dtype=np.int32)
+    for t in tiles:
+        cover[t["ref_bgn"]:t["ref_end"] + 1, t["hash_bgn"]:t["hash_end"] + 1] += 1
+    r, h = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    need = (r >= 1) & (h >= 1) & (r < h)
+    assert (cover[need] == 1).all()
+
+
+def test_assignment_is_balanced_and_deterministic():
+    from canu_b200 import api
+    tiles = api.plan_tiles(_lens("A"), 500, 40000, 60000)
+    assert len(tiles) > 20
+    for w in (1, 2, 4, 8):
+        own = api.assign_tiles(tiles, w)
+        assert own == api.assign_tiles(tiles, w)
+        load = np.zeros(w)
+        for t, o in zip(tiles, own):
+            load[o] += t["cost"]
+        assert set(own) == set(range(w))
+        assert load.max() <= load.mean() * 1.25 + max(t["cost"] for t in tiles)
+
+
+def test_tiles_over_two_gloo_ranks_reproduce_the_single_tile(tmp_path):
+    """world_size 2 on gloo: each rank runs (with the oracle) only the tiles it owns; the gathered union must be
+    the reference's golden output for the whole range, and the counters must add up."""
+    script = os.path.join(ROOT, "tests", "gloo_tiles_worker.py")
+    out = str(tmp_path / "result.json")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29571", script, out]
+    r = subprocess.run(cmd, env=env, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    res = json.load(open(out))
+    assert res["world"] == 2 and res["tiles"] > 4
+    assert min(res["tiles_per_rank"]) > 0
+    assert res["records_match_golden"], res
+    assert res["stats_match_golden"], res
