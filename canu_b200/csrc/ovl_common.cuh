@@ -47,6 +47,28 @@ OVL_HD int ovl_match16(uint64_t a, uint64_t b) {
   return z ? (ovl_ctz64(z) >> 2) : 16;
 }
 
+//  32-bit flavour for the DP inner loop: 8 bases per test (most cells of a noisy band stop within 2 bases).
+OVL_HD int ovl_match8(uint32_t a, uint32_t b) {
+  uint32_t t = a & b;
+  uint32_t z = (t - 0x11111111u) & ~t & 0x88888888u;
+#if defined(__CUDA_ARCH__)
+  return z ? ((__ffs((int)z) - 1) >> 2) : 8;
+#else
+  return z ? (__builtin_ctz(z) >> 2) : 8;
+#endif
+}
+
+//  8 nibbles starting at base x (x >= 0); w32 is the same dp4 storage viewed as 32-bit words.
+OVL_HD uint32_t ovl_fetch8(const uint32_t *w32, int x) {
+  const uint32_t *p = w32 + (x >> 3);
+  const int sh = (x & 7) << 2;
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(p[0], p[1], sh);
+#else
+  return sh ? ((p[0] >> sh) | (p[1] << (32 - sh))) : p[0];
+#endif
+}
+
 //  Number of leading nibble positions at which a == b exactly, 0..16 (for seeds: N never seeds).
 OVL_HD int ovl_equal16(uint64_t a, uint64_t b) {
   uint64_t x = a ^ b;

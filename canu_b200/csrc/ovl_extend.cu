@@ -189,6 +189,7 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
 
   int *prev = M.sring0, *cur = M.sring1;
   uint32_t mask = SRING - 1;
+  const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
   bool in_shared = true;
   if (lane == 0) prev[0] = row0;
   int L = 0, R = 0;
@@ -222,21 +223,28 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     __syncwarp();
 
     int term_d = 0x7fffffff, term_row = 0;
+    //  band pruning and best-cell bookkeeping are folded into the cell loop (forward.C:245-299): a cell survives
+    //  the pruning iff EA[e][d] + max(d,0) >= Edit_Match_Limit[e]; the new band is [min, max] surviving d, and the
+    //  longest cell of that band is always a surviving one (a pruned cell inside the band is shorter than the
+    //  nearest survivor on its left), so one pass over the row gives Left, Right, Longest and Best_d.
+    const int lim_e = P.eml[e];
+    int mn = 0x7fffffff, mx = -0x7fffffff, bv = -1, bd = 0x7fffffff;
     for (uint32_t g = 0; g < ngroups; g++) {
       const int d = Lu + (int)(g << 5) + lane;
       const bool act = d <= Ru;
       int row = 0, code = 0, lim = 0, cnt = 0;
       bool more = false;
       if (act) {
-        int a = prev[(d - 1) & mask], b = prev[d & mask], c2 = prev[(d + 1) & mask];
+        const uint32_t i0 = (uint32_t)(d - 1) & mask;
+        const int a = prev[i0], b = prev[(i0 + 1) & mask], c2 = prev[(i0 + 2) & mask];
         row = 1 + b;
         if (a > row) { row = a; code = 1; }
         if (1 + c2 > row) { row = 1 + c2; code = 2; }
         lim = min(m - row, n - d - row);
         if (lim > 0) {
-          //  every lane slides its own diagonal over the first 16 bases ...
-          cnt = ovl_match16(ovl_fetch16(A, a0 + row), ovl_fetch16(T, t0 + row + d));
-          more = (cnt == 16) && (lim > 16);
+          //  every lane slides its own diagonal over the first 8 bases (32-bit arithmetic) ...
+          cnt = ovl_match8(ovl_fetch8(A32, a0 + row), ovl_fetch8(T32, t0 + row + d));
+          more = (cnt == 8) && (lim > 8);
           if (cnt > lim) cnt = lim;
         }
       }
@@ -245,12 +253,16 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
       for (unsigned pend = __ballot_sync(FULL, more); pend; pend &= pend - 1) {
         const int l = __ffs(pend) - 1;
         const int r_l = __shfl_sync(FULL, row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, lim, l);
-        const int ext = warp_slide(A, a0 + r_l + 16, T, t0 + r_l + d_l + 16, lim_l - 16, lane);
-        if (lane == l) cnt = 16 + ext;
+        const int ext = warp_slide(A, a0 + r_l + 8, T, t0 + r_l + d_l + 8, lim_l - 8, lane);
+        if (lane == l) cnt = 8 + ext;
       }
       if (act) {
         row += cnt;
         cur[d & mask] = row;
+        if (!(row + (d > 0 ? d : 0) < lim_e)) {
+          mn = min(mn, d); mx = max(mx, d);
+          if (row > bv) { bv = row; bd = d; }
+        }
       }
       unsigned b0 = __ballot_sync(FULL, act && (code & 1));
       unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
@@ -296,23 +308,10 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     cells += (unsigned long long)width;
     aoff += ngroups;
 
-    //  prune the band edges (forward.C:245-280): P(d) = EA[e][d] + max(d,0) < Edit_Match_Limit[e]
-    const int lim_e = P.eml[e];
-    int mn = 0x7fffffff, mx = -0x7fffffff;
-    for (int d = Lu + lane; d <= Ru; d += 32) {
-      int v = cur[d & mask];
-      if (!(v + (d > 0 ? d : 0) < lim_e)) { mn = min(mn, d); mx = max(mx, d); }
-    }
     mn = __reduce_min_sync(FULL, mn);
     mx = __reduce_max_sync(FULL, mx);
     if (mn > mx) break;                               // Left > Right
     L = mn; R = mx;
-
-    int bv = -1, bd = 0x7fffffff;
-    for (int d = L + lane; d <= R; d += 32) {
-      int v = cur[d & mask];
-      if (v > bv) { bv = v; bd = d; }
-    }
     int vmax = __reduce_max_sync(FULL, bv);
     int dmin = __reduce_min_sync(FULL, bv == vmax ? bd : 0x7fffffff);
     if (vmax > longest) { longest = vmax; best_d = dmin; best_e = e; }

@@ -3,7 +3,10 @@
 //                                                (--packed: through the zero-decode 2-bit path)
 //    ovltool dump-ovb <file.ovb>                 records as "a b dat0 dat1" (hex words) on stdout
 //    ovltool rewrite-ovb <in.ovb> <out.ovb> <lastReadID>   decode with our snappy reader, write with our writer
+//    ovltool cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]        canonical sort + compare, exit 0 iff identical
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -82,6 +85,39 @@ int main(int argc, char **argv) {
     if (!W.close(err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     return 0;
   }
-  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID>\n");
+  if (argc >= 4 && !strcmp(argv[1], "cmp-ovb")) {
+    //  canonical-sort both files (ovOverlap::operator<, stores/ovOverlap.H:263-276) and compare record by record;
+    //  optional 4th argument: a read ID whose records are ignored on both sides (the reference's last-ref-read quirk)
+    std::vector<ovlb_record> A, B;
+    if (!read_ovb(argv[2], A, err) || !read_ovb(argv[3], B, err)) { fprintf(stderr, "%s\n", err.c_str()); return 2; }
+    const uint32_t ignore = argc >= 5 ? (uint32_t)strtoul(argv[4], nullptr, 10) : 0;
+    auto drop = [&](std::vector<ovlb_record> &v) {
+      if (!ignore) return;
+      size_t k = 0;
+      for (auto &r : v) if (r.a_iid != ignore && r.b_iid != ignore) v[k++] = r;
+      v.resize(k);
+    };
+    drop(A); drop(B);
+    auto lt = [](const ovlb_record &x, const ovlb_record &y) {
+      if (x.a_iid != y.a_iid) return x.a_iid < y.a_iid;
+      if (x.b_iid != y.b_iid) return x.b_iid < y.b_iid;
+      if (x.dat0 != y.dat0) return x.dat0 < y.dat0;
+      return x.dat1 < y.dat1;
+    };
+    std::sort(A.begin(), A.end(), lt); std::sort(B.begin(), B.end(), lt);
+    size_t i = 0, j = 0, onlyA = 0, onlyB = 0, shown = 0;
+    while (i < A.size() || j < B.size()) {
+      if (j == B.size() || (i < A.size() && lt(A[i], B[j]))) {
+        if (shown++ < 10) printf("only-first  %u %u %016lx %016lx\n", A[i].a_iid, A[i].b_iid, (unsigned long)A[i].dat0, (unsigned long)A[i].dat1);
+        onlyA++; i++;
+      } else if (i == A.size() || lt(B[j], A[i])) {
+        if (shown++ < 10) printf("only-second %u %u %016lx %016lx\n", B[j].a_iid, B[j].b_iid, (unsigned long)B[j].dat0, (unsigned long)B[j].dat1);
+        onlyB++; j++;
+      } else { i++; j++; }
+    }
+    printf("first %zu second %zu only-first %zu only-second %zu\n", A.size(), B.size(), onlyA, onlyB);
+    return (onlyA || onlyB) ? 1 : 0;
+  }
+  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
   return 1;
 }
