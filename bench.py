@@ -243,11 +243,17 @@ def main():
     pairs_step = ctr["pairs"] / args.steps
     cells_step = ctr["dp_cells"] / args.steps
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with HOST buffers: packed reads are copied host->device for the hash side and
+    #      again for the ref side, overlap records device->host, every step; host buffers are page-locked
+    packed.pin()
+    rec_host = np.zeros(max(n_rec, 1) + 1024, dtype=api.RECORD_DTYPE)
+    api._check(api.load_library().ovlb_host_register(rec_host.ctypes.data, rec_host.nbytes))
+
     def e2e_step():
         ov.load_hash_reads(packed)
         ov.build_index()
-        return ov.overlap_ref_batch(packed, cap=max(n_rec, 1) + 1024)
+        k = ov.overlap_ref_batch_into(packed, rec_host)
+        return rec_host[:k]
 
     e2e_step()
     barrier()
@@ -275,24 +281,37 @@ def main():
     if rank == 0:
         peaks, which = measured_peaks()
         # dominant stage of the step and its roofline (DESIGN.md "Kernels and rooflines" states the per-unit bytes)
-        stages = {k2: v2 for k2, v2 in stage_ms.items() if k2 in ("index_tuples_ms", "index_sort_ms", "index_table_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms")}
-        dom = max(stages, key=stages.get)
+        # stage times are CUDA-event brackets on the library's stream around each kernel (group) of the step
+        hbm_stages = ("index_tuples_ms", "index_sort_ms", "index_table_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms")
+        stages = {k2: v2 for k2, v2 in stage_ms.items() if k2 in hbm_stages + ("extend_ms",)}
+        dom_all = max(stages, key=stages.get)
+        dom = max((k2 for k2 in stages if k2 in hbm_stages), key=stages.get)
         hk, rk, sh, sr = (ctr[x] / args.steps for x in ("hash_kmers", "ref_kmers", "seed_hits", "seed_runs"))
         # algorithmic bytes per unit: DESIGN.md section 4
         alg_bytes = {
             "index_tuples_ms": hk * (0.5 + 12),                     # dp4 base read + (key, position) tuple write
             "index_sort_ms": hk * 12 * 2,                            # one read + one write of every 12 B tuple (a single-pass partition)
-            "index_table_ms": hk * 8 + ctr["hash_kmers"] * 0,        # sorted keys read once (+ 32 B per distinct k-mer, not counted)
+            "index_table_ms": hk * 8,                                # sorted keys read once (+ 32 B per distinct k-mer, not counted)
             "probe_ms": rk * (0.5 + 32),                             # dp4 base + one 32 B slot sector per window
             "expand_ms": sr * (4 + 16 + 16),                         # occurrence + bases compared + run record written
             "sort_ms": sr * 16 * 2,                                  # one read + one write of every 16 B run record
             "chain_ms": sr * (16 + 12 + 12 + 16),
-            "extend_ms": cells_step * 0.25,                          # 2-bit from-codes are the only HBM traffic per cell
         }[dom]
         achieved = alg_bytes / (stages[dom] * 1e-3) / 1e9
+        # DRAM traffic of that kernel per launch from the committed ncu --set full capture of this same workload
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.genome == 5_000_000 and args.coverage == 50.0:
+            traffic = json.load(open(tpath)).get(dom.replace("_ms", ""))
         roofline = {"bound": "hbm", "kernel": dom.replace("_ms", ""), "achieved": achieved, "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                    "ms_per_launch": stages[dom]}
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
+                    "ms_per_launch": stages[dom], "dominant_stage_of_step": dom_all.replace("_ms", ""),
+                    "note": "dominant HBM-bound kernel of the step; the extension kernel is integer-ALU bound and is reported under 'extension'"}
+        if dom == "probe_ms":
+            # a random 32 B probe costs a whole 128 B line on B200 and the memory system sustains 36.9 G of them per second
+            # (tools/micro/rand_sector.cu, profiles/README.md): the practical ceiling of any hash probe
+            roofline["random_access"] = {"achieved_gaccess_s": rk / (stages[dom] * 1e-3) / 1e9, "peak_gaccess_s": 36.9,
+                                         "frac": rk / (stages[dom] * 1e-3) / 1e9 / 36.9}
         line = {
             "metric": "ovl read-pairs aligned/sec", "value": pairs_all / (ms_step * 1e-3), "unit": "read-pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,

@@ -76,7 +76,7 @@ EXPORTS = [
     "ovlb_last_error", "ovlb_device_count", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
-    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_debug_pairs", "ovlb_debug_extend",
+    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
     "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_assign_tiles",
 ]
@@ -107,6 +107,8 @@ def load_library():
     L.ovlb_get_timings.argtypes = [C.c_void_p, C.POINTER(_Timings)]
     L.ovlb_kernel_launches.argtypes = [C.c_void_p]
     L.ovlb_kernel_launches.restype = C.c_uint64
+    L.ovlb_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.ovlb_host_unregister.argtypes = [C.c_void_p]
     L.ovlb_timer_start.argtypes = [C.c_void_p]
     L.ovlb_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.ovlb_debug_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
@@ -174,8 +176,20 @@ class PackedReads:
         self.total_bases = int(np.where(lens >= min_len, lens, 0).sum())
         self.packed_bytes = int(self.view.contents.packed_bytes)
 
+    def pin(self):
+        """Page-lock the packed bases and the per-read arrays (faster, asynchronous uploads)."""
+        L = load_library()
+        v = self.view.contents
+        self._pinned = [p for p, n in ((v.packed, v.packed_bytes), (v.byte_offset, 8 * v.n_reads), (v.len, 4 * v.n_reads)) if p and n]
+        for p, n in ((v.packed, v.packed_bytes), (v.byte_offset, 8 * v.n_reads), (v.len, 4 * v.n_reads)):
+            if p and n:
+                _check(L.ovlb_host_register(p, n))
+
     def close(self):
         if self._h:
+            for p in getattr(self, "_pinned", []):
+                load_library().ovlb_host_unregister(p)
+            self._pinned = []
             load_library().ovlb_reads_free(self._h)
             self._h = C.c_void_p()
 
@@ -243,6 +257,12 @@ class Overlapper:
         _check(self.L.ovlb_build_index(self._h))
 
     # --- ref side ---
+    def overlap_ref_batch_into(self, packed: PackedReads, out: np.ndarray) -> int:
+        """Same as overlap_ref_batch but into a caller-owned (e.g. pinned) record array; returns the count."""
+        n = C.c_uint64()
+        _check(self.L.ovlb_overlap_ref_batch(self._h, C.cast(packed.view, C.c_void_p), out.ctypes.data, out.size, C.byref(n)))
+        return n.value
+
     def overlap_ref_batch(self, packed: PackedReads, cap: int = 1 << 20) -> np.ndarray:
         out = np.zeros(cap, dtype=RECORD_DTYPE)
         n = C.c_uint64()

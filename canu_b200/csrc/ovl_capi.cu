@@ -226,6 +226,21 @@ int ovlb_get_timings(ovlb_ctx *c, ovlb_timings *out) {
 
 uint64_t ovlb_kernel_launches(ovlb_ctx *c) { return c ? c->launches : 0; }
 
+int ovlb_host_register(const void *ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return OVLB_OK;
+  cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), (size_t)bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return OVLB_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); ovl_set_error(std::string("cudaHostRegister: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; }
+  return OVLB_OK;
+}
+
+int ovlb_host_unregister(const void *ptr) {
+  if (!ptr) return OVLB_OK;
+  cudaError_t e = cudaHostUnregister(const_cast<void *>(ptr));
+  if (e != cudaSuccess) { cudaGetLastError(); if (e != cudaErrorHostMemoryNotRegistered) { ovl_set_error(std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; } }
+  return OVLB_OK;
+}
+
 int ovlb_timer_start(ovlb_ctx *c) {
   if (!c) { ovl_set_error("ovlb_timer_start: null context"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));

@@ -171,6 +171,12 @@ uint64_t ovlb_kernel_launches(ovlb_ctx *ctx);   /* kernels launched by this cont
 int  ovlb_timer_start(ovlb_ctx *ctx);
 int  ovlb_timer_stop(ovlb_ctx *ctx, float *ms);
 
+/*  Page-lock (pin) a caller-owned host buffer so that the copies in ovlb_load_hash_reads /
+ *  ovlb_stage_ref_batch / ovlb_fetch_records run at full PCIe/NVLink-C2C speed and asynchronously.
+ *  Optional: every call also accepts pageable memory.  */
+int  ovlb_host_register(const void *ptr, uint64_t bytes);
+int  ovlb_host_unregister(const void *ptr);
+
 /*  Kernel-granularity debug taps used by the parity tests (tests/ only).  After
  *  ovlb_run_staged()/ovlb_overlap_ref_batch() the candidate pairs and their
  *  ordered seed lists (the reference's String_Olap_t / Match_Node_t lists just
