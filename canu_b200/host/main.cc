@@ -78,6 +78,9 @@ static void usage(const char *argv0) {
   fprintf(stderr, "--hashblock n      bases of hash reads per device-resident index\n\n");
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct Phase { double create = 0, pack_hash = 0, index = 0, pack_ref = 0, stage = 0, run = 0, fetch = 0; };
+
 #define FAIL(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } while (0)
 
 //  Pack reads bgn..end (inclusive) of the store into the wire format.  Reads outside the library
@@ -279,6 +282,8 @@ int main(int argc, char **argv) {
 
   //  One worker thread per GPU; tiles share nothing, records go to the one writer thread, counters are summed.
   std::vector<ovlb_counters> counters(W);
+  std::vector<Phase> phase(W);
+  const double t_setup_done = now_s();
   std::vector<std::string> werr(W);
   std::mutex log_mu;
   auto worker = [&](uint32_t wi) {
@@ -287,7 +292,10 @@ int main(int argc, char **argv) {
     SqStore st;                                                         // the reader is stateful: one per thread
     if (!st.open(G.storePath, err)) { werr[wi] = err; return; }
     ovlb_ctx *ctx = nullptr;
+    Phase &ph = phase[wi];
+    double t0 = now_s();
     if (ovlb_create(G.gpus[wi], &P, &ctx)) { werr[wi] = ovlb_last_error(); return; }
+    ph.create += now_s() - t0;
     Packed HB, RB;
     uint32_t curHb = 0, curHe = 0;
     std::vector<ovlb_record> recs;
@@ -296,11 +304,14 @@ int main(int argc, char **argv) {
       if (owner[ti] != wi) continue;
       const ovlb_tile &T = tiles[ti];
       if (T.hash_bgn != curHb || T.hash_end != curHe) {
+        t0 = now_s();
         if (!pack_range(st, T.hash_bgn, T.hash_end, G.minLibToHash, G.maxLibToHash, minLen, HB, err)) { werr[wi] = err; break; }
+        ph.pack_hash += now_s() - t0; t0 = now_s();
         { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Build_Hash_Index from %u to %u (%lu bases)\n", G.gpus[wi], T.hash_bgn, T.hash_end, (unsigned long)HB.bases); }
         if (ovlb_load_hash_reads(ctx, &HB.view) ||
             (!skip.empty() && ovlb_mark_skip_kmers(ctx, skip.data(), skip.size())) ||
             ovlb_build_index(ctx)) { werr[wi] = ovlb_last_error(); break; }
+        ph.index += now_s() - t0;
         curHb = T.hash_bgn; curHe = T.hash_end;
       }
       //  only ref reads with ID below the last hash read can produce pairs (refID < hashID)
@@ -310,10 +321,14 @@ int main(int argc, char **argv) {
       while (!todo.empty() && werr[wi].empty()) {
         const uint32_t rb = todo.back().first, r2 = todo.back().second;
         todo.pop_back();
+        t0 = now_s();
         if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RB, err)) { werr[wi] = err; break; }
+        ph.pack_ref += now_s() - t0; t0 = now_s();
         uint64_t n = 0;
         int rc = (r2 - rb + 1 > 200000) ? OVLB_ERR_CAPACITY : ovlb_stage_ref_batch(ctx, &RB.view);
+        ph.stage += now_s() - t0; t0 = now_s();
         if (!rc) rc = ovlb_run_staged(ctx, &n);
+        ph.run += now_s() - t0; t0 = now_s();
         if (rc == OVLB_ERR_CAPACITY && r2 > rb) {                       // seed buffers overflowed: halve the batch
           const uint32_t mid = rb + (r2 - rb) / 2;
           todo.push_back({mid + 1, r2}); todo.push_back({rb, mid});
@@ -322,6 +337,7 @@ int main(int argc, char **argv) {
         if (rc) { werr[wi] = ovlb_last_error(); break; }
         recs.resize(n);
         if (ovlb_fetch_records(ctx, recs.data(), recs.size(), &n)) { werr[wi] = ovlb_last_error(); break; }
+        ph.fetch += now_s() - t0;
         { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", G.gpus[wi], rb, r2, T.hash_bgn, T.hash_end, (unsigned long)RB.bases, (unsigned long)n); }
         out.submit(std::move(recs));
         recs = std::vector<ovlb_record>();
@@ -345,8 +361,15 @@ int main(int argc, char **argv) {
     uint64_t *dst = reinterpret_cast<uint64_t *>(&C);
     for (size_t k = 0; k < sizeof(ovlb_counters) / 8; k++) dst[k] += src[k];
   }
+  const double t_workers_done = now_s();
   if (!out.close(e)) FAIL("ERROR: %s", e.c_str());
   ovlb_params_free(&P);
+  const double t_closed = now_s();
+  fprintf(stderr, "phases (s): setup %.2f | workers %.2f | writer drain %.2f\n",
+          t_setup_done - std::chrono::duration<double>(t_start.time_since_epoch()).count(), t_workers_done - t_setup_done, t_closed - t_workers_done);
+  for (uint32_t wi = 0; wi < W; wi++)
+    fprintf(stderr, "  [gpu %d] create %.2f  pack-hash %.2f  load+index %.2f  pack-ref %.2f  stage %.2f  run %.2f  fetch %.2f\n", G.gpus[wi],
+            phase[wi].create, phase[wi].pack_hash, phase[wi].index, phase[wi].pack_ref, phase[wi].stage, phase[wi].run, phase[wi].fetch);
 
   FILE *stats = stderr;
   if (G.statName) {

@@ -30,6 +30,11 @@ CASES = {
     "S4b": (200_000, 40, 0.06, "0.12", ("uniform", 3000, 12000), [], "-pacbio"),
     "S4c": (150_000, 40, 0.075, "0.15", ("uniform", 3000, 12000), [], "-pacbio"),
     "S5": (1_000_000, 30, 0.01, "0.045", ("uniform", 3000, 15000), ["-partial"], "-pacbio"),  # obt mode
+    # planted 4 kb x 40-copy repeat + its k-mers as the -k skip list (Mark_Skip_Kmers, hopeless check on)
+    "S6": (1_000_000, 30, 0.01, "0.045", ("uniform", 3000, 15000), ["SKIP"], "-pacbio"),
+    "C1full": (4_600_000, 30, 0.01, "0.045", ("uniform", 3000, 15000), [], "-pacbio"),     # BASELINE configs[0] at full size
+    "C2full": (5_000_000, 50, 0.001, "0.01", ("lognormal", 9.25, 0.3), [], "-pacbio-hifi"),  # BASELINE configs[1] at full size
+    "S7": (800_000, 30, 0.02, "0.06", ("uniform", 3000, 15000), ["SKIP", "--minkmers"], "-pacbio"),
 }
 
 
@@ -50,7 +55,7 @@ def pick_threads(n_reads, cores):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--cases", default=",".join(k for k in CASES if not k.endswith("full")))
     ap.add_argument("--out", default="")
     ap.add_argument("--gpus", default="0")
     args = ap.parse_args()
@@ -61,7 +66,9 @@ def main():
         G, cov, err, erate, lm, extra, tech = CASES[name]
         wd = tempfile.mkdtemp(prefix="ovlparity_")
         try:
-            g = synth.make_genome(G, seed=11)
+            use_skip = "SKIP" in extra
+            extra = [x for x in extra if x != "SKIP"]
+            g = synth.make_genome(G, seed=11, repeat_len=4000 if use_skip else 0, repeat_copies=40 if use_skip else 0)
             if lm[0] == "uniform":
                 reads = synth.simulate_reads(g, cov, lm[1], lm[2], err, seed=12)
             else:
@@ -71,6 +78,15 @@ def main():
             subprocess.check_call([os.path.join(REF, "sqStoreCreate"), "-o", st, "-minlength", "1000", tech, "lib", fa],
                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             n = len(reads)
+            if use_skip:
+                # what `meryl print` would list: every k-mer of the repeat unit (high count), one per line with a count
+                step = G // 40
+                unit = g[step // 3: step // 3 + 4000].tobytes().decode()
+                skipf = os.path.join(wd, "skip.dump")
+                with open(skipf, "w") as f:
+                    for i in range(0, len(unit) - 22 + 1):
+                        f.write("%s\t%d\n" % (unit[i:i + 22], 40 * cov))
+                extra = ["-k", skipf] + extra
             t = pick_threads(n, cores)
             common = ["-k", "22", "--hashbits", "23", "--hashload", "0.8", "--hashdatalen", str(10 ** 10), "--maxerate", erate,
                       "--minlength", "500", "-h", "1-%d" % n, "-r", "1-%d" % n] + extra
