@@ -2,6 +2,7 @@
 #include "ovl_ctx.h"
 
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 
 static thread_local std::string g_last_error;
@@ -76,6 +77,8 @@ int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   c->dp.erate = p->max_erate; c->dp.bmv = p->branch_match_value; c->dp.min_tail_slope = p->min_branch_tail_slope;
   c->dp.minkmers_factor = p->minkmers_exp_factor;
   c->dp.eml = c->d_eml; c->dp.n_eml = p->n_edit_match_limit;
+  c->dp.ext_prefetch = 1;
+  if (const char *ev = getenv("OVLB_EXT_PREFETCH")) c->dp.ext_prefetch = atoi(ev);
   memset(&c->timings, 0, sizeof(c->timings));
   *out = c;
   return OVLB_OK;

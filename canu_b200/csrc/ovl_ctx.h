@@ -65,6 +65,7 @@ struct DevParams {                // kernel-visible job parameters
   double    erate, bmv, min_tail_slope, minkmers_factor;
   const int32_t *eml;             // Edit_Match_Limit
   uint32_t  n_eml;
+  int       ext_prefetch;         // tuning: 0 none, 1 L1, 2 L2 prefetch of the read lines ahead of the DP wavefront
 };
 
 //  Per-warp scratch of the extension kernel.

@@ -22,24 +22,50 @@
 //  Integer DP: no tensor cores.  The only floating point is the branch-point score, evaluated once
 //  per row in FP64 with separate multiply and subtract (the reference build has no FMA).
 #include "ovl_ctx.h"
+#include <cstdlib>
 
 #define EXT_WARPS  8
 #define EXT_THREADS (EXT_WARPS * 32)
 #define SRING      512                    // ints per shared ring (per row, per warp)
 #define FULL       0xffffffffu
 
-struct WarpMem {
-  int      *sring0, *sring1;              // shared rings
-  int      *gring0, *gring1;              // HBM rings
-  uint32_t  gring_cap;
-  uint2    *arena;  uint64_t arena_cap;
+struct DpOut { int a_end, t_end, errors, leftover, match_to_end, delta_len; };
+
+//  Everything a warp needs that is the same in all 32 lanes lives ONCE per warp in shared memory: scratch pointers, the
+//  result of the last extension, the overlaps collected for the current pair, statistics.  Kept in per-thread variables
+//  these were spilled to local memory (696 B of stack per thread = 530 KB per SM at 24 warps), which evicted the read
+//  data from L1 and put an L2 round trip behind every access (ncu: 42 % long-scoreboard stalls, most of them after LDL).
+struct WarpCtl {
+  int      *gring0, *gring1;              // HBM rings (bands wider than the shared ring)
+  uint2    *arena;                        // from-code bit planes
   int32_t  *row_left; uint32_t *row_off;
   uint8_t  *path; int32_t *ival; uint32_t *ikc;
   int32_t  *ldelta, *rdelta;
+  uint64_t  arena_cap;
+  uint32_t  gring_cap;
   int       emax;
+  DpOut     o;                            // result of the last warp_dp
+  const uint64_t *s_fwd, *s_rc, *t_fwd, *t_rc;   // current pair: ref read in its search orientation (and its reverse complement), hash read
+  int       s_len, t_len;
+  uint32_t  s_id, t_id;
+  int64_t   seed_begin;
+  int       n_seeds, dir, consistent;
+  int       distinct_ct;
+  OvlOlap   distinct[OVL_MAX_DISTINCT_OLAPS];
+  unsigned long long cells, calls, c_with, c_without, c_multi, c_total, c_cont, c_dove;
 };
 
-struct DpOut { int a_end, t_end, errors, leftover, match_to_end, delta_len; };
+//  dynamic shared memory of the extension kernels: | DevParams | WarpCtl x EXT_WARPS | rings: EXT_WARPS x 2 x SRING ints |
+#define EXT_SM_PARAMS 0
+#define EXT_SM_CTL    128
+#define EXT_SM_RINGS  (EXT_SM_CTL + ((EXT_WARPS * (int)sizeof(WarpCtl) + 127) / 128) * 128)
+#define EXT_SM_BYTES  (EXT_SM_RINGS + EXT_WARPS * 2 * SRING * 4)
+static_assert(sizeof(DevParams) <= EXT_SM_CTL, "DevParams must fit its shared-memory slot");
+extern __shared__ __align__(16) unsigned char ext_sm[];
+
+__device__ __forceinline__ const DevParams &sh_params() { return *reinterpret_cast<const DevParams *>(ext_sm + EXT_SM_PARAMS); }
+__device__ __forceinline__ WarpCtl &sh_ctl() { return reinterpret_cast<WarpCtl *>(ext_sm + EXT_SM_CTL)[threadIdx.x >> 5]; }
+__device__ __forceinline__ int *sh_ring(int which) { return reinterpret_cast<int *>(ext_sm + EXT_SM_RINGS) + ((threadIdx.x >> 5) * 2 + which) * SRING; }
 
 //  Number of leading positions (< lim) where A[a..] and T[t..] match; all 32 lanes cooperate, 512 bases per round.
 __device__ __forceinline__ int warp_slide(const uint64_t *A, int a, const uint64_t *T, int t, int lim, int lane) {
@@ -58,18 +84,39 @@ __device__ __forceinline__ int warp_slide(const uint64_t *A, int a, const uint64
   return total < lim ? total : lim;
 }
 
+//  Pull the read lines the DP is about to walk over into L1 (mode 1) or L2 (mode 2): lanes 0..15 take 16 consecutive
+//  128-byte lines (256 bases each) of A starting at the line of base `a`, lanes 16..31 the same for T.  On HiFi-like
+//  reads an extension is a chain of dependent row -> slide -> row steps, each waiting a full DRAM round trip for bases
+//  that lie a few hundred bytes further down the same two reads; one burst of prefetches per ~4 kb turns all but the
+//  first of those waits into L1 hits.  Lines past the end of the read (`a_end`, `t_end`: exclusive base limits) are skipped.
+#define PF_SPAN 3840                      // bases certainly covered by one burst (15 whole lines)
+__device__ __forceinline__ void dp_prefetch(int mode, const uint64_t *A, int a, int a_end, const uint64_t *T, int t, int t_end, int lane) {
+  const bool is_t = lane >= 16;
+  const uintptr_t base = (uintptr_t)(is_t ? T : A);
+  int from = is_t ? t : a; if (from < 0) from = 0;
+  const int end = is_t ? t_end : a_end;
+  const uintptr_t p = ((base + ((uintptr_t)from >> 1)) & ~(uintptr_t)127) + 128u * (uint32_t)(lane & 15);
+  if (p < base + (((uintptr_t)end + 1) >> 1)) {
+    if (mode == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    else           asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+  }
+}
+
 //  i-th value pushed by Set_Right_Delta / Set_Left_Delta's loop (k descending): V_i = row value below indel i.
-__device__ __forceinline__ int push_at(const WarpMem &M, int i, int v_start) {
-  int vi = M.ival[i];
-  int vp = (i == 0) ? v_start : M.ival[i - 1];
-  return ((M.ikc[i] >> 30) == 1u) ? (vi - vp - 1) : (vp - vi);
+__device__ __forceinline__ int push_at(const int32_t *ival, const uint32_t *ikc, int i, int v_start) {
+  int vi = ival[i];
+  int vp = (i == 0) ? v_start : ival[i - 1];
+  return ((ikc[i] >> 30) == 1u) ? (vi - vp - 1) : (vp - vi);
 }
 
 //  Traceback through the from-codes, then delta encoding.  Returns delta_len; writes deltas to `out`.
 //  fwd_rules: Set_Right_Delta conventions; else Set_Left_Delta (sets leftover, may bump t_mag).
-__device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+__device__ __noinline__ int warp_traceback(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                               int e_start, int d_start, int v_start, int row0, bool fwd_rules, int first_code,
-                              int32_t *out, int &leftover, int &t_mag, int lane) {
+                              int32_t *out, int lane) {
+  WarpCtl &C = sh_ctl();
+  const int32_t *row_left = C.row_left; const uint32_t *row_off = C.row_off; const uint2 *arena = C.arena;
+  uint8_t *path = C.path; int32_t *ival = C.ival; uint32_t *ikc = C.ikc;
   //  Phase A: walk down, 32 rows per round
   int n_ind = 0;
   int dcur = d_start;
@@ -77,11 +124,11 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
     const int kk = kb - lane;                      // my row
     int rl = 0; uint32_t glo = 0; uint2 w0 = make_uint2(0, 0), w1 = w0, w2 = w0;
     if (kk >= 1) {
-      rl = M.row_left[kk];
-      uint32_t ro = M.row_off[kk];
+      rl = row_left[kk];
+      uint32_t ro = row_off[kk];
       int idx_lo = dcur - lane - rl; if (idx_lo < 0) idx_lo = 0;
       glo = (uint32_t)idx_lo >> 5;
-      const uint2 *ap = M.arena + ro + glo;
+      const uint2 *ap = arena + ro + glo;
       w0 = ap[0]; w1 = ap[1]; w2 = ap[2];
     }
     int mycode = 0;
@@ -101,11 +148,11 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
       if (lane == l) mycode = code;
       if (code == 1) dcur--; else if (code == 2) dcur++;
     }
-    if (kk >= 1) M.path[kk] = (uint8_t)mycode;
+    if (kk >= 1) path[kk] = (uint8_t)mycode;
     unsigned im = __ballot_sync(FULL, kk >= 1 && mycode != 0);
     if (kk >= 1 && mycode != 0) {
       int idx = n_ind + __popc(im & ((1u << lane) - 1));
-      M.ikc[idx] = (uint32_t)kk | ((uint32_t)mycode << 30);
+      ikc[idx] = (uint32_t)kk | ((uint32_t)mycode << 30);
     }
     n_ind += __popc(im);
   }
@@ -116,13 +163,13 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
     int v = row0, d = 0, seen = 0;
     for (int kb = 1; kb <= e_start; kb += 32) {
       int myc = 0;
-      if (kb + lane <= e_start) myc = M.path[kb + lane];
+      if (kb + lane <= e_start) myc = path[kb + lane];
       const int steps = (e_start - kb + 1) < 32 ? (e_start - kb + 1) : 32;
       for (int l = 0; l < steps; l++) {
         const int k = kb + l;
         const int c = __shfl_sync(FULL, myc, l);
         if (c != 0) {
-          if (lane == 0) M.ival[n_ind - 1 - seen] = v;
+          if (lane == 0) ival[n_ind - 1 - seen] = v;
           seen++;
         }
         if (k == e_start || seen == n_ind) { kb = e_start + 1; break; }   // nothing above the last indel is needed
@@ -136,8 +183,8 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
   __syncwarp();
 
   //  Phase C: deltas.  push_i = (code 1) ? V_i - V_{i-1} - 1 : V_{i-1} - V_i, with V_{-1} = v_start.
-  const int last = n_ind ? M.ival[n_ind - 1] : v_start;
-#define PUSH(i) push_at(M, (i), v_start)
+  const int last = n_ind ? ival[n_ind - 1] : v_start;
+#define PUSH(i) push_at(ival, ikc, (i), v_start)
   int len = n_ind;
   if (fwd_rules) {
     //  stack S[0..n_ind-1] = pushes, S[n_ind] = last+1;  Right_Delta[j] = |S[n_ind-j]| * sign(S[n_ind-j-1])
@@ -149,7 +196,7 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
       out[j] = a * ((sim > 0) - (sim < 0));
     }
   } else {
-    leftover = last;
+    int t_mag = C.o.t_end;
     bool fix = false;
     if (n_ind > 1) {
       int p0 = PUSH(0);
@@ -165,6 +212,8 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
     } else {
       for (int j = lane; j < n_ind; j += 32) out[j] = PUSH(j);
     }
+    __syncwarp();
+    if (lane == 0) { C.o.leftover = last; C.o.t_end = t_mag; }
   }
 #undef PUSH
   __syncwarp();
@@ -176,18 +225,24 @@ __device__ __noinline__ int warp_traceback(WarpMem &M, const uint64_t *A, int a0
 //  Deliberately NOT inlined: the kernel calls it from four places (right/left extension x which read is the
 //  shorter one); one shared copy keeps the kernel's code inside the instruction cache (the fully inlined
 //  version was 17.6 k SASS instructions and spent 79 % of its stall samples waiting for instruction fetch).
-__device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
-                        int error_limit, bool fwd_rules, int32_t *delta_out, DpOut &o,
-                        unsigned long long &cells, unsigned long long &calls, unsigned long long *err_flags, int lane) {
+__device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+                        int error_limit, bool fwd_rules, unsigned long long *err_flags, int lane) {
+  const DevParams &P = sh_params();
+  WarpCtl &C = sh_ctl();
+  DpOut &o = C.o;                                    // every lane stores the same values
+  unsigned int cells = 0;
+  __syncwarp();                                      // every lane has read the previous extension's result
   o.leftover = 0; o.delta_len = 0;
+  int pf_next = PF_SPAN;
+  if (P.ext_prefetch) dp_prefetch(P.ext_prefetch, A, a0, a0 + m, T, t0, t0 + n, lane);
   int row0 = warp_slide(A, a0, T, t0, m, lane);
   if (row0 == m) {                                   // exact match to the end of A
     o.a_end = m; o.t_end = m; o.leftover = m; o.match_to_end = 1; o.errors = 0;
     return;
   }
-  calls++;
+  if (lane == 0) C.calls++;
 
-  int *prev = M.sring0, *cur = M.sring1;
+  int *prev = sh_ring(0), *cur = sh_ring(1);
   uint32_t mask = SRING - 1;
   const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
   bool in_shared = true;
@@ -197,7 +252,6 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
   int ms_len = 0, ms_d = 0, ms_e = 0;
   double max_score = 0.0;
   uint32_t aoff = 0;
-  const double bmv = P.bmv;
   int e;
   bool reached_end = false;
   int tb_e = 0, tb_d = 0, tb_v = 0, first_code = -1;
@@ -207,18 +261,19 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     const int Lu = L - 1, Ru = R + 1;
     const int width = Ru - Lu + 1;
     if (in_shared && width + 4 > SRING) {            // migrate the previous row to the HBM ring
-      for (int d = L + lane; d <= R; d += 32) M.gring0[d & (M.gring_cap - 1)] = prev[d & mask];
+      int *g0 = C.gring0; const uint32_t gmask = C.gring_cap - 1;
+      for (int d = L + lane; d <= R; d += 32) g0[d & gmask] = prev[d & mask];
       __syncwarp();
-      prev = M.gring0; cur = M.gring1; mask = M.gring_cap - 1; in_shared = false;
+      prev = g0; cur = C.gring1; mask = gmask; in_shared = false;
     }
     const uint32_t ngroups = (uint32_t)(width + 31) >> 5;
-    if ((!in_shared && (uint32_t)(width + 4) > M.gring_cap) || (uint64_t)aoff + ngroups + 4 > M.arena_cap || e > M.emax) {
+    if ((!in_shared && (uint32_t)(width + 4) > mask + 1) || (uint64_t)aoff + ngroups + 4 > C.arena_cap || e > C.emax) {
       if (lane == 0) atomicOr(err_flags, 4ull);       // scratch too small: reported as an error by the host
       break;
     }
     if (lane == 0) {
       prev[(L - 1) & mask] = -2; prev[(L - 2) & mask] = -2; prev[(R + 1) & mask] = -2; prev[(R + 2) & mask] = -2;
-      M.row_left[e] = Lu; M.row_off[e] = aoff;
+      C.row_left[e] = Lu; C.row_off[e] = aoff;
     }
     __syncwarp();
 
@@ -266,7 +321,7 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
       }
       unsigned b0 = __ballot_sync(FULL, act && (code & 1));
       unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
-      if (lane == 0) M.arena[aoff + g] = make_uint2(b0, b1);
+      if (lane == 0) C.arena[aoff + g] = make_uint2(b0, b1);
       unsigned hb = __ballot_sync(FULL, act && (row == m || row + d == n));
       if (hb) {
         int tl = __ffs(hb) - 1;
@@ -278,9 +333,9 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     __syncwarp();
 
     if (term_d != 0x7fffffff) {
-      cells += (unsigned long long)(term_d - Lu + 1);
+      cells += (unsigned int)(term_d - Lu + 1);
       //  reached the end of A or T: branch-point test (forward.C:170-212)
-      double score = __dsub_rn(__dmul_rn((double)term_row, bmv), (double)e);
+      double score = __dsub_rn(__dmul_rn((double)term_row, P.bmv), (double)e);
       int tail_len = term_row - ms_len;
       bool abort_ = false;
       if (P.partial && score < max_score) abort_ = true;
@@ -305,7 +360,7 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
       reached_end = true;
       break;
     }
-    cells += (unsigned long long)width;
+    cells += (unsigned int)width;
     aoff += ngroups;
 
     mn = __reduce_min_sync(FULL, mn);
@@ -315,8 +370,12 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     int vmax = __reduce_max_sync(FULL, bv);
     int dmin = __reduce_min_sync(FULL, bv == vmax ? bd : 0x7fffffff);
     if (vmax > longest) { longest = vmax; best_d = dmin; best_e = e; }
+    if (P.ext_prefetch && longest + 1536 > pf_next) {
+      dp_prefetch(P.ext_prefetch, A, a0 + pf_next, a0 + m, T, t0 + pf_next + best_d, t0 + n, lane);
+      pf_next += PF_SPAN;
+    }
 
-    double score = __dsub_rn(__dmul_rn((double)longest, bmv), (double)e);
+    double score = __dsub_rn(__dmul_rn((double)longest, P.bmv), (double)e);
     if (score > max_score) { max_score = score; ms_len = longest; ms_d = best_d; ms_e = best_e; }
 
     int *t = prev; prev = cur; cur = t;
@@ -328,39 +387,40 @@ __device__ __noinline__ void warp_dp(const DevParams &P, WarpMem &M, const uint6
     o.a_end = ms_len; o.t_end = ms_len + ms_d; o.match_to_end = 0; o.errors = ms_e;
     tb_e = ms_e; tb_d = ms_d; tb_v = (ms_e == 0) ? row0 : ms_len;
   }
-  o.delta_len = warp_traceback(M, A, a0, m, T, t0, n, tb_e, tb_d, tb_v, row0, fwd_rules, first_code, delta_out, o.leftover, o.t_end, lane);
+  if (lane == 0) C.cells += cells;
+  __syncwarp();
+  const int dl = warp_traceback(A, a0, m, T, t0, n, tb_e, tb_d, tb_v, row0, fwd_rules, first_code, fwd_rules ? C.rdelta : C.ldelta, lane);
+  o.delta_len = dl;
 }
-
-struct ReadView {
-  const uint64_t *fwd, *rc;     // dp4 words of this read, forward and reverse complement
-  int len;
-};
 
 //  Extend_Alignment (prefixEditDistance-extend.C:36-183).  S is the ref read in its search orientation
 //  (S.fwd = oriented sequence, S.rc = its reverse complement); T the hash read.
-//  On return M.ldelta[0..ldelta_len) is the merged Left_Delta.
-__device__ int warp_extend_alignment(const DevParams &P, WarpMem &M, const ReadView &S, const ReadView &T,
-                                     int m_start, int m_offset, int m_len,
+//  On return ldelta[0..ldelta_len) (the warp's ldelta scratch) is the merged Left_Delta.
+__device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
                                      int &s_lo, int &s_hi, int &t_lo, int &t_hi, int &errors, int &ldelta_len,
-                                     unsigned long long &cells, unsigned long long &calls, unsigned long long *err_flags, int lane) {
+                                     unsigned long long *err_flags, int lane) {
+  const DevParams &P = sh_params();
+  WarpCtl &C = sh_ctl();
   int right_errors = 0, left_errors = 0, leftover = 0;
   bool r_to_end = true, l_to_end = true;
-  const int s_left_begin = m_start - 1, s_right_begin = m_start + m_len, s_right_len = S.len - s_right_begin;
-  const int t_left_begin = m_offset - 1, t_right_begin = m_offset + m_len, t_right_len = T.len - t_right_begin;
+  const int S_len = C.s_len, T_len = C.t_len;
+  const int s_left_begin = m_start - 1, s_right_begin = m_start + m_len, s_right_len = S_len - s_right_begin;
+  const int t_left_begin = m_offset - 1, t_right_begin = m_offset + m_len, t_right_len = T_len - t_right_begin;
   const int total_olap = min(m_start, m_offset) + m_len + min(s_right_len, t_right_len);
   const int error_limit = (int)ceil(__dmul_rn((double)total_olap, P.erate));      // Error_Bound[Total_Olap]
 
   int rlen = 0, llen = 0;
   bool r_negate = false, l_negate = false;
-  DpOut o;
 
   if (s_right_len == 0 || t_right_len == 0) {
     s_hi = 0; t_hi = 0;
   } else if (s_right_len <= t_right_len) {
-    warp_dp(P, M, S.fwd, s_right_begin, s_right_len, T.fwd, t_right_begin, t_right_len, error_limit, true, M.rdelta, o, cells, calls, err_flags, lane);
+    warp_dp(C.s_fwd, s_right_begin, s_right_len, C.t_fwd, t_right_begin, t_right_len, error_limit, true, err_flags, lane);
+    const DpOut o = C.o;
     right_errors = o.errors; s_hi = o.a_end; t_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len; r_negate = true;
   } else {
-    warp_dp(P, M, T.fwd, t_right_begin, t_right_len, S.fwd, s_right_begin, s_right_len, error_limit, true, M.rdelta, o, cells, calls, err_flags, lane);
+    warp_dp(C.t_fwd, t_right_begin, t_right_len, C.s_fwd, s_right_begin, s_right_len, error_limit, true, err_flags, lane);
+    const DpOut o = C.o;
     right_errors = o.errors; t_hi = o.a_end; s_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len;
   }
   s_hi += s_right_begin - 1;
@@ -370,12 +430,14 @@ __device__ int warp_extend_alignment(const DevParams &P, WarpMem &M, const ReadV
     s_lo = 0; t_lo = 0;
   } else if (s_right_begin <= t_right_begin) {
     //  reverse(S + s_left_begin, ...) == forward on the reverse complements, starting at the mirrored position
-    warp_dp(P, M, S.rc, S.len - 1 - s_left_begin, s_left_begin + 1, T.rc, T.len - 1 - t_left_begin, t_left_begin + 1,
-            error_limit - right_errors, false, M.ldelta, o, cells, calls, err_flags, lane);
+    warp_dp(C.s_rc, S_len - 1 - s_left_begin, s_left_begin + 1, C.t_rc, T_len - 1 - t_left_begin, t_left_begin + 1,
+            error_limit - right_errors, false, err_flags, lane);
+    const DpOut o = C.o;
     left_errors = o.errors; s_lo = -o.a_end; t_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
   } else {
-    warp_dp(P, M, T.rc, T.len - 1 - t_left_begin, t_left_begin + 1, S.rc, S.len - 1 - s_left_begin, s_left_begin + 1,
-            error_limit - right_errors, false, M.ldelta, o, cells, calls, err_flags, lane);
+    warp_dp(C.t_rc, T_len - 1 - t_left_begin, t_left_begin + 1, C.s_rc, S_len - 1 - s_left_begin, s_left_begin + 1,
+            error_limit - right_errors, false, err_flags, lane);
+    const DpOut o = C.o;
     left_errors = o.errors; t_lo = -o.a_end; s_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
     l_negate = true;
   }
@@ -387,13 +449,14 @@ __device__ int warp_extend_alignment(const DevParams &P, WarpMem &M, const ReadV
 
   //  merge: Left_Delta (sign-flipped when T played "A"), then the right deltas, negated (extend.C:164-175)
   __syncwarp();
-  if (l_negate) for (int i = lane; i < llen; i += 32) M.ldelta[i] = -M.ldelta[i];
+  int32_t *ldelta = C.ldelta; const int32_t *rdelta = C.rdelta;
+  if (l_negate) for (int i = lane; i < llen; i += 32) ldelta[i] = -ldelta[i];
   for (int i = lane; i < rlen; i += 32) {
-    int rd = M.rdelta[i]; if (r_negate) rd = -rd;
+    int rd = rdelta[i]; if (r_negate) rd = -rd;
     int v;
     if (i == 0) v = (rd > 0) ? -(rd + leftover + m_len) : -(rd - leftover - m_len);
     else        v = -rd;
-    M.ldelta[llen + i] = v;
+    ldelta[llen + i] = v;
   }
   ldelta_len = llen + rlen;
   __syncwarp();
@@ -495,23 +558,30 @@ __device__ void choose_best_partial(OvlOlap *o, int ct, int *deleted) {         
   for (int i = 0; i < ct; i++) deleted[i] = (i != best);
 }
 
-__device__ __forceinline__ void bind_warp_mem(WarpMem &M, const ExtScratch &X, int *sm, int warp_in_block, int gwarp) {
-  M.sring0 = sm + (size_t)warp_in_block * 2 * SRING;
-  M.sring1 = M.sring0 + SRING;
-  M.gring_cap = X.gring_cap;
-  M.gring0 = X.gring + (size_t)gwarp * 2 * X.gring_cap;
-  M.gring1 = M.gring0 + X.gring_cap;
-  M.arena = X.arena + (size_t)gwarp * X.arena_cap;  M.arena_cap = X.arena_cap;
-  const size_t st = (size_t)X.emax + 2;
-  M.row_left = X.row_left + gwarp * st;  M.row_off = X.row_off + gwarp * st;
-  M.path = X.path + gwarp * st;  M.ival = X.ival + gwarp * st;  M.ikc = X.ikc + gwarp * st;
-  M.ldelta = X.ldelta + gwarp * st;  M.rdelta = X.rdelta + gwarp * st;
-  M.emax = X.emax;
+//  CTA prologue: thread 0 publishes the job parameters, lane 0 of every warp binds the warp's scratch.
+__device__ __forceinline__ void bind_warp_ctl(const DevParams &P, const ExtScratch &X, int gwarp) {
+  if (threadIdx.x == 0) *reinterpret_cast<DevParams *>(ext_sm + EXT_SM_PARAMS) = P;
+  if ((threadIdx.x & 31) == 0 && gwarp < X.n_warps) {
+    WarpCtl &C = sh_ctl();
+    C.gring_cap = X.gring_cap;
+    C.gring0 = X.gring + (size_t)gwarp * 2 * X.gring_cap;
+    C.gring1 = C.gring0 + X.gring_cap;
+    C.arena = X.arena + (size_t)gwarp * X.arena_cap;  C.arena_cap = X.arena_cap;
+    const size_t st = (size_t)X.emax + 2;
+    C.row_left = X.row_left + gwarp * st;  C.row_off = X.row_off + gwarp * st;
+    C.path = X.path + gwarp * st;  C.ival = X.ival + gwarp * st;  C.ikc = X.ikc + gwarp * st;
+    C.ldelta = X.ldelta + gwarp * st;  C.rdelta = X.rdelta + gwarp * st;
+    C.emax = X.emax;
+    C.distinct_ct = 0;
+    C.cells = C.calls = C.c_with = C.c_without = C.c_multi = C.c_total = C.c_cont = C.c_dove = 0;
+  }
+  __syncthreads();
 }
 
 //  Persistent kernel: warps pull pairs from a global cursor (pairs differ wildly in cost).
-__global__ void __launch_bounds__(EXT_THREADS, 3)
-k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uint64_t n_pairs,
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(EXT_THREADS, MIN_BLOCKS)
+k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, uint64_t n_pairs,
                const int32_t *__restrict__ seed_start, const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_len,
                uint8_t *seed_alive,
                const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff,
@@ -519,15 +589,12 @@ k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uin
                const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hrc, const uint64_t *__restrict__ hwoff,
                const uint32_t *__restrict__ hlen, uint32_t hash_first_id,
                ovlb_record *records, uint64_t rec_cap, unsigned long long *work, unsigned long long *counters) {
-  extern __shared__ int sm[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int gwarp = blockIdx.x * EXT_WARPS + wib;
+  const int gwarp = blockIdx.x * EXT_WARPS + (threadIdx.x >> 5);
+  bind_warp_ctl(P_, X, gwarp);
   if (gwarp >= X.n_warps) return;
-  WarpMem M;
-  bind_warp_mem(M, X, sm, wib, gwarp);
-
-  unsigned long long cells = 0, calls = 0, c_with = 0, c_without = 0, c_multi = 0, c_total = 0, c_cont = 0, c_dove = 0;
+  const DevParams &P = sh_params();
+  WarpCtl &C = sh_ctl();
   unsigned long long *err_flags = &counters[CT_ERR_FLAGS];
 
   while (true) {
@@ -538,19 +605,22 @@ k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uin
     const PairRec pr = pairs[pi];
     if (pr.n_seeds == 0) continue;
 
-    ReadView S, T;
-    S.len = (int)rlen[pr.ref_idx];
-    S.fwd = (pr.dir ? rrc : rfwd) + rwoff[pr.ref_idx];
-    S.rc  = (pr.dir ? rfwd : rrc) + rwoff[pr.ref_idx];
-    T.len = (int)hlen[pr.hash_idx];
-    T.fwd = hfwd + hwoff[pr.hash_idx];
-    T.rc  = hrc + hwoff[pr.hash_idx];
-    const uint32_t s_id = ref_first_id + pr.ref_idx, t_id = hash_first_id + pr.hash_idx;
+    __syncwarp();
+    if (lane == 0) {
+      const uint64_t rw = rwoff[pr.ref_idx], hw = hwoff[pr.hash_idx];
+      C.s_len = (int)rlen[pr.ref_idx];
+      C.s_fwd = (pr.dir ? rrc : rfwd) + rw;
+      C.s_rc  = (pr.dir ? rfwd : rrc) + rw;
+      C.t_len = (int)hlen[pr.hash_idx];
+      C.t_fwd = hfwd + hw;
+      C.t_rc  = hrc + hw;
+      C.s_id = ref_first_id + pr.ref_idx; C.t_id = hash_first_id + pr.hash_idx;
+      C.seed_begin = pr.seed_begin; C.n_seeds = pr.n_seeds; C.dir = pr.dir; C.consistent = pr.consistent;
+      C.distinct_ct = 0;
+    }
+    __syncwarp();
     const int64_t sb = pr.seed_begin;
     const int ns = pr.n_seeds;
-
-    OvlOlap distinct[OVL_MAX_DISTINCT_OLAPS];
-    int distinct_ct = 0;
     int remaining = ns;
 
     while (remaining > 0) {
@@ -567,20 +637,20 @@ k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uin
       const int m_start = seed_start[sb + li], m_offset = seed_off[sb + li], m_len = seed_len[sb + li];
 
       int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
-      const int kind = warp_extend_alignment(P, M, S, T, m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len,
-                                             cells, calls, err_flags, lane);
+      const int kind = warp_extend_alignment(m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len, err_flags, lane);
 
       const bool usable = (kind == OVL_DOVETAIL) || P.partial;
-      if (usable && 1 + s_hi - s_lo >= P.min_olap_len && 1 + t_hi - t_lo >= P.min_olap_len) {
+      if (lane == 0 && usable && 1 + s_hi - s_lo >= P.min_olap_len && 1 + t_hi - t_lo >= P.min_olap_len) {
         int olap_len = 1 + min(s_hi - s_lo, t_hi - t_lo);
         double quality = __ddiv_rn((double)errors, (double)olap_len);
         if (errors <= (int)ceil(__dmul_rn((double)olap_len, P.erate)))
-          add_overlap(P, s_lo, s_hi, t_lo, t_hi, quality, ld_len, distinct, distinct_ct);
+          add_overlap(P, s_lo, s_hi, t_lo, t_hi, quality, ld_len, C.distinct, C.distinct_ct);
       }
 
-      if (pr.consistent) break;                       // all remaining seeds are dropped (:473-474)
+      if (C.consistent) break;                        // all remaining seeds are dropped (:473-474)
 
       //  remove the seed just used and every seed lying on the alignment (:476-490)
+      const int32_t *ldelta = C.ldelta;
       int removed = 0;
       for (int i0 = 0; i0 < ns; i0 += 32) {
         const int i = i0 + lane;
@@ -590,7 +660,7 @@ k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uin
           else if (usable) {
             int st = seed_start[sb + i], ln = seed_len[sb + i];
             if (s_lo - OVL_SHIFT_SLACK <= st && st + ln <= (s_hi + 1) + OVL_SHIFT_SLACK - 1 &&
-                lies_on_alignment(M.ldelta, ld_len, st, seed_off[sb + i], s_lo, t_lo))
+                lies_on_alignment(ldelta, ld_len, st, seed_off[sb + i], s_lo, t_lo))
               rm = true;
           }
           if (rm) seed_alive[sb + i] = 0;
@@ -601,85 +671,89 @@ k_extend_pairs(DevParams P, ExtScratch X, const PairRec *__restrict__ pairs, uin
       __syncwarp();
     }
 
-    int outputs = 0;
-    if (distinct_ct > 0) {
-      int deleted[OVL_MAX_DISTINCT_OLAPS] = {0, 0, 0};
-      if (P.partial) { if (P.unique) choose_best_partial(distinct, distinct_ct, deleted); }
-      else           { if (P.unique) combine_into_one(distinct, distinct_ct, deleted); else merge_intersecting(distinct, distinct_ct, deleted); }
-      for (int i = 0; i < distinct_ct; i++)
-        if (!deleted[i]) {
-          uint32_t a, b; uint64_t w0, w1;
-          if (P.partial) {
-            ovl_output_partial(s_id, t_id, pr.dir, distinct[i], S.len, T.len, &a, &b, &w0, &w1);
-          } else {
-            int cont = ovl_output_overlap(s_id, S.len, pr.dir, t_id, T.len, distinct[i], &a, &b, &w0, &w1);
-            if (cont) c_cont++; else c_dove++;
-          }
-          c_total++;
-          if (lane == 0) {
+    //  Combine / merge / choose and output: warp-uniform scalar work, done by lane 0
+    if (lane == 0) {
+      const int distinct_ct = C.distinct_ct;
+      OvlOlap *distinct = C.distinct;
+      int outputs = 0;
+      if (distinct_ct > 0) {
+        int deleted[OVL_MAX_DISTINCT_OLAPS] = {0, 0, 0};
+        if (P.partial) { if (P.unique) choose_best_partial(distinct, distinct_ct, deleted); }
+        else           { if (P.unique) combine_into_one(distinct, distinct_ct, deleted); else merge_intersecting(distinct, distinct_ct, deleted); }
+        for (int i = 0; i < distinct_ct; i++)
+          if (!deleted[i]) {
+            uint32_t a, b; uint64_t w0, w1;
+            if (P.partial) {
+              ovl_output_partial(C.s_id, C.t_id, C.dir, distinct[i], C.s_len, C.t_len, &a, &b, &w0, &w1);
+            } else {
+              int cont = ovl_output_overlap(C.s_id, C.s_len, C.dir, C.t_id, C.t_len, distinct[i], &a, &b, &w0, &w1);
+              if (cont) C.c_cont++; else C.c_dove++;
+            }
+            C.c_total++;
             unsigned long long ri = atomicAdd(&work[2], 1ull);
             if (ri < rec_cap) { ovlb_record r; r.a_iid = a; r.b_iid = b; r.dat0 = w0; r.dat1 = w1; records[ri] = r; }
             else atomicOr(err_flags, 2ull);
+            outputs++;
           }
-          outputs++;
-        }
+      }
+      if (outputs == 0) C.c_without++;
+      else { C.c_with++; if (outputs > 1) C.c_multi++; }
     }
-    if (outputs == 0) c_without++;
-    else { c_with++; if (outputs > 1) c_multi++; }
   }
 
   if (lane == 0) {
-    if (c_without) atomicAdd(&counters[CT_HITS_WITHOUT], c_without);
-    if (c_with)    atomicAdd(&counters[CT_HITS_WITH], c_with);
-    if (c_multi)   atomicAdd(&counters[CT_MULTI], c_multi);
-    if (c_total)   atomicAdd(&counters[CT_TOTAL], c_total);
-    if (c_cont)    atomicAdd(&counters[CT_CONTAINED], c_cont);
-    if (c_dove)    atomicAdd(&counters[CT_DOVETAIL], c_dove);
-    if (cells)     atomicAdd(&counters[CT_DP_CELLS], cells);
-    if (calls)     atomicAdd(&counters[CT_EXT_CALLS], calls);
+    if (C.c_without) atomicAdd(&counters[CT_HITS_WITHOUT], C.c_without);
+    if (C.c_with)    atomicAdd(&counters[CT_HITS_WITH], C.c_with);
+    if (C.c_multi)   atomicAdd(&counters[CT_MULTI], C.c_multi);
+    if (C.c_total)   atomicAdd(&counters[CT_TOTAL], C.c_total);
+    if (C.c_cont)    atomicAdd(&counters[CT_CONTAINED], C.c_cont);
+    if (C.c_dove)    atomicAdd(&counters[CT_DOVETAIL], C.c_dove);
+    if (C.cells)     atomicAdd(&counters[CT_DP_CELLS], C.cells);
+    if (C.calls)     atomicAdd(&counters[CT_EXT_CALLS], C.calls);
   }
 }
 
 //  Debug tap: one warp per explicit seed; out7 = s_lo, s_hi, t_lo, t_hi, errors, kind, delta_ct.
 __global__ void __launch_bounds__(EXT_THREADS)
-k_debug_extend(DevParams P, ExtScratch X, uint32_t n, const uint32_t *__restrict__ ref_index, const int32_t *__restrict__ dir,
+k_debug_extend(DevParams P_, ExtScratch X, uint32_t n, const uint32_t *__restrict__ ref_index, const int32_t *__restrict__ dir,
                const uint32_t *__restrict__ hash_index, const int32_t *__restrict__ m_start, const int32_t *__restrict__ m_offset,
                const int32_t *__restrict__ m_len,
                const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff, const uint32_t *__restrict__ rlen,
                const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hrc, const uint64_t *__restrict__ hwoff, const uint32_t *__restrict__ hlen,
                int32_t *out7, int32_t *deltas, uint32_t delta_stride, unsigned long long *work, unsigned long long *counters) {
-  extern __shared__ int sm[];
   const int lane = threadIdx.x & 31;
-  const int wib = threadIdx.x >> 5;
-  const int gwarp = blockIdx.x * EXT_WARPS + wib;
+  const int gwarp = blockIdx.x * EXT_WARPS + (threadIdx.x >> 5);
+  bind_warp_ctl(P_, X, gwarp);
   if (gwarp >= X.n_warps) return;
-  WarpMem M;
-  bind_warp_mem(M, X, sm, wib, gwarp);
-  unsigned long long cells = 0, calls = 0;
+  WarpCtl &C = sh_ctl();
   while (true) {
     unsigned long long i = 0;
     if (lane == 0) i = atomicAdd(&work[1], 1ull);
     i = __shfl_sync(FULL, i, 0);
     if (i >= n) break;
-    ReadView S, T;
     const uint32_t ri = ref_index[i], hi = hash_index[i];
     const int dr = dir[i];
-    S.len = (int)rlen[ri]; S.fwd = (dr ? rrc : rfwd) + rwoff[ri]; S.rc = (dr ? rfwd : rrc) + rwoff[ri];
-    T.len = (int)hlen[hi]; T.fwd = hfwd + hwoff[hi]; T.rc = hrc + hwoff[hi];
+    __syncwarp();
+    if (lane == 0) {
+      C.s_len = (int)rlen[ri]; C.s_fwd = (dr ? rrc : rfwd) + rwoff[ri]; C.s_rc = (dr ? rfwd : rrc) + rwoff[ri];
+      C.t_len = (int)hlen[hi]; C.t_fwd = hfwd + hwoff[hi]; C.t_rc = hrc + hwoff[hi];
+    }
+    __syncwarp();
     int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
-    int kind = warp_extend_alignment(P, M, S, T, m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
-                                     cells, calls, &counters[CT_ERR_FLAGS], lane);
+    int kind = warp_extend_alignment(m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
+                                     &counters[CT_ERR_FLAGS], lane);
     if (lane == 0) {
       int32_t *o = out7 + 7 * i;
       o[0] = s_lo; o[1] = s_hi; o[2] = t_lo; o[3] = t_hi; o[4] = errors; o[5] = kind; o[6] = ld_len;
     }
+    const int32_t *ldelta = C.ldelta;
     if (deltas)
-      for (int j = lane; j < ld_len && j < (int)delta_stride; j += 32) deltas[(size_t)i * delta_stride + j] = M.ldelta[j];
+      for (int j = lane; j < ld_len && j < (int)delta_stride; j += 32) deltas[(size_t)i * delta_stride + j] = ldelta[j];
     __syncwarp();
   }
   if (lane == 0) {
-    if (cells) atomicAdd(&counters[CT_DP_CELLS], cells);
-    if (calls) atomicAdd(&counters[CT_EXT_CALLS], calls);
+    if (C.cells) atomicAdd(&counters[CT_DP_CELLS], C.cells);
+    if (C.calls) atomicAdd(&counters[CT_EXT_CALLS], C.calls);
   }
 }
 
@@ -728,8 +802,10 @@ int ovl_prepare_ext_scratch(ovlb_ctx *c) {
   CK(cudaMalloc((void **)&X.ldelta, want_warps * st * 4));
   CK(cudaMalloc((void **)&X.rdelta, want_warps * st * 4));
   c->ext = X;
-  const int smem = EXT_WARPS * 2 * SRING * 4;
-  CK(cudaFuncSetAttribute(k_extend_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = EXT_SM_BYTES;
+  CK(cudaFuncSetAttribute(k_extend_pairs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_extend_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(k_extend_pairs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_debug_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OVLB_OK;
 }
@@ -746,15 +822,20 @@ int ovl_extend_pairs(ovlb_ctx *c) {
     CK(cudaMalloc((void **)&c->d_records, want * sizeof(ovlb_record)));
     c->rec_cap = want;
   }
-  const int smem = EXT_WARPS * 2 * SRING * 4;
+  const int smem = EXT_SM_BYTES;
   int blocks = c->ext.n_warps / EXT_WARPS;
   uint64_t need_blocks = (c->n_pairs + EXT_WARPS - 1) / EXT_WARPS;
   if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
-  k_extend_pairs<<<blocks, EXT_THREADS, smem, c->stream>>>(
-      c->dp, c->ext, c->pairs, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive,
-      c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->ref.first_id,
-      c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len, c->hash.first_id,
-      c->d_records, c->rec_cap, c->d_work, c->d_counters->v);
+  static int min_blocks = 0;
+  if (!min_blocks) { const char *ev = getenv("OVLB_EXT_BLOCKS"); min_blocks = ev ? atoi(ev) : 4; if (min_blocks < 2 || min_blocks > 4) min_blocks = 4; }
+  if ((uint64_t)c->sm_count * min_blocks < (uint64_t)blocks) blocks = c->sm_count * min_blocks;
+#define EXT_LAUNCH(MB) k_extend_pairs<MB><<<blocks, EXT_THREADS, smem, c->stream>>>( \
+      c->dp, c->ext, c->pairs, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \
+      c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->ref.first_id, \
+      c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len, c->hash.first_id, \
+      c->d_records, c->rec_cap, c->d_work, c->d_counters->v)
+  if (min_blocks == 2) EXT_LAUNCH(2); else if (min_blocks == 4) EXT_LAUNCH(4); else EXT_LAUNCH(3);
+#undef EXT_LAUNCH
   c->launches++;
   CK(cudaGetLastError());
   return OVLB_OK;
@@ -777,7 +858,7 @@ int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const i
   CK(cudaMemcpyAsync(d_i + 2 * n, seed_offset, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d_i + 3 * n, seed_len, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->d_work, 0, 64, c->stream));
-  const int smem = EXT_WARPS * 2 * SRING * 4;
+  const int smem = EXT_SM_BYTES;
   int blocks = c->ext.n_warps / EXT_WARPS;
   uint64_t need_blocks = ((uint64_t)n + EXT_WARPS - 1) / EXT_WARPS;
   if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
