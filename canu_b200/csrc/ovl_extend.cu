@@ -220,12 +220,89 @@ __device__ __noinline__ int warp_traceback(const uint64_t *A, int a0, int m, con
   return len;
 }
 
+//  The cells of one error row: 32 diagonals per round.  SH = the two row rings live in shared memory (bands up to
+//  SRING-4 wide), addressed from the kernel's shared-memory symbol so that the compiler emits LDS/STS; otherwise
+//  they are the warp's HBM rings.  `psel` says which of the two rings holds row e-1.
+//  Ring layout: a row computed for diagonals [Lu, Ru] is stored at index d - Lu + 2 (no modular wrap: a row is
+//  at most ring size - 4 wide), so cell d of the next row finds EA[e-1][d-1], [d], [d+1] in three consecutive
+//  words at index d - pbase + 1, `pbase` being the Lu of the row below; `pidx` = Lu - pbase + 1.
+//  Band pruning and best-cell bookkeeping are folded into the cell loop (forward.C:245-299): a cell survives the
+//  pruning iff EA[e][d] + max(d,0) >= Edit_Match_Limit[e]; the new band is [min, max] surviving d, and the longest
+//  cell of that band is always a surviving one (a pruned cell inside the band is shorter than the nearest survivor
+//  on its left), so one pass over the row gives Left, Right, Longest and Best_d.
+struct RowOut { int mn, mx, bv, bd, term_d, term_row; };
+
+template <bool SH>
+__device__ __forceinline__ void dp_row_cells(int psel, int pidx, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+                                             int Lu, int Ru, uint32_t ngroups, int lim_e, uint2 *arena_row, int lane, RowOut &ro) {
+  const int *prev; int *cur;
+  if (SH) { int *ring = sh_ring(0); prev = ring + psel * SRING; cur = ring + (psel ^ 1) * SRING; }
+  else    { WarpCtl &C = sh_ctl(); prev = psel ? C.gring1 : C.gring0; cur = psel ? C.gring0 : C.gring1; }
+  const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
+  int mn = 0x7fffffff, mx = -0x7fffffff, bv = -1, bd = 0x7fffffff;
+  ro.term_d = 0x7fffffff; ro.term_row = 0;
+  prev += pidx + lane; cur += 2 + lane;
+  for (uint32_t g = 0; g < ngroups; g++, prev += 32, cur += 32) {
+    const int d = Lu + (int)(g << 5) + lane;
+    const bool act = d <= Ru;
+    int row = 0, code = 0, lim = 0, cnt = 0;
+    bool more = false;
+    if (act) {
+      const int a = prev[0], b = prev[1], c2 = prev[2];
+      row = 1 + b;
+      if (a > row) { row = a; code = 1; }
+      if (1 + c2 > row) { row = 1 + c2; code = 2; }
+      lim = min(m - row, n - d - row);
+      if (lim > 0) {
+        //  every lane slides its own diagonal over the first 8 bases (32-bit arithmetic) ...
+        cnt = ovl_match8(ovl_fetch8(A32, a0 + row), ovl_fetch8(T32, t0 + row + d));
+        more = (cnt == 8) && (lim > 8);
+        if (cnt > lim) cnt = lim;
+      }
+    }
+    //  ... and the few diagonals that are still matching (on real overlaps: the true one) are finished by the
+    //  whole warp, 512 bases per round, instead of one lane chasing dependent loads
+    for (unsigned pend = __ballot_sync(FULL, more); pend; pend &= pend - 1) {
+      const int l = __ffs(pend) - 1;
+      const int r_l = __shfl_sync(FULL, row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, lim, l);
+      const int ext = warp_slide(A, a0 + r_l + 8, T, t0 + r_l + d_l + 8, lim_l - 8, lane);
+      if (lane == l) cnt = 8 + ext;
+    }
+    if (act) {
+      row += cnt;
+      cur[0] = row;
+      if (!(row + (d > 0 ? d : 0) < lim_e)) {
+        mn = min(mn, d); mx = max(mx, d);
+        if (row > bv) { bv = row; bd = d; }
+      }
+    }
+    const unsigned b0 = __ballot_sync(FULL, act && (code & 1));
+    const unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
+    if (lane == 0) arena_row[g] = make_uint2(b0, b1);
+    const unsigned hb = __ballot_sync(FULL, act && (row == m || row + d == n));
+    if (hb) {
+      const int tl = __ffs(hb) - 1;
+      ro.term_d = Lu + (int)(g << 5) + tl;
+      ro.term_row = __shfl_sync(FULL, row, tl);
+      break;
+    }
+  }
+  ro.mn = mn; ro.mx = mx; ro.bv = bv; ro.bd = bd;
+}
+
+#ifdef OVL_DP_NOINLINE
+#define OVL_DP_LINKAGE __noinline__
+#else
+#define OVL_DP_LINKAGE __forceinline__
+#endif
+
 //  One banded extension (forward(), or reverse() on reverse-complemented strings).
 //  A: shorter string (m <= n), starting at base a0 of the dp4 words A; T likewise.
-//  Deliberately NOT inlined: the kernel calls it from four places (right/left extension x which read is the
-//  shorter one); one shared copy keeps the kernel's code inside the instruction cache (the fully inlined
-//  version was 17.6 k SASS instructions and spent 79 % of its stall samples waiting for instruction fetch).
-__device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
+//  It has exactly ONE call site (the side loop of warp_extend_alignment), so inlining it does not duplicate it:
+//  an earlier version called it from four places and, fully inlined, was 17.6 k SASS instructions that spent 79 % of
+//  their stall samples waiting for instruction fetch; as a separate function every memory access re-materialised
+//  its descriptor (R2UR) from the call ABI's vector registers.
+__device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                         int error_limit, bool fwd_rules, unsigned long long *err_flags, int lane) {
   const DevParams &P = sh_params();
   WarpCtl &C = sh_ctl();
@@ -242,11 +319,11 @@ __device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uin
   }
   if (lane == 0) C.calls++;
 
-  int *prev = sh_ring(0), *cur = sh_ring(1);
-  uint32_t mask = SRING - 1;
-  const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
+  int psel = 0;                                      // ring holding row e-1
+  int pbase = 0;                                     // diagonal stored at index 2 of that ring
+  uint32_t rcap = SRING;
   bool in_shared = true;
-  if (lane == 0) prev[0] = row0;
+  if (lane == 0) sh_ring(0)[2] = row0;
   int L = 0, R = 0;
   int longest = 0, best_d = 0, best_e = 0;
   int ms_len = 0, ms_d = 0, ms_e = 0;
@@ -261,75 +338,30 @@ __device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uin
     const int Lu = L - 1, Ru = R + 1;
     const int width = Ru - Lu + 1;
     if (in_shared && width + 4 > SRING) {            // migrate the previous row to the HBM ring
-      int *g0 = C.gring0; const uint32_t gmask = C.gring_cap - 1;
-      for (int d = L + lane; d <= R; d += 32) g0[d & gmask] = prev[d & mask];
+      int *g0 = psel ? C.gring1 : C.gring0;
+      const int *sp = sh_ring(psel);
+      for (int i = lane; i <= R - pbase + 4; i += 32) g0[i] = sp[i];
       __syncwarp();
-      prev = g0; cur = C.gring1; mask = gmask; in_shared = false;
+      rcap = C.gring_cap; in_shared = false;
     }
     const uint32_t ngroups = (uint32_t)(width + 31) >> 5;
-    if ((!in_shared && (uint32_t)(width + 4) > mask + 1) || (uint64_t)aoff + ngroups + 4 > C.arena_cap || e > C.emax) {
+    if ((!in_shared && (uint32_t)(width + 4) > rcap) || (uint64_t)aoff + ngroups + 4 > C.arena_cap || e > C.emax) {
       if (lane == 0) atomicOr(err_flags, 4ull);       // scratch too small: reported as an error by the host
       break;
     }
+    //  generic pointer (rare accesses only), biased so that prev[d] = EA[e-1][d]
+    int *prev = (in_shared ? sh_ring(psel) : (psel ? C.gring1 : C.gring0)) + (2 - pbase);
     if (lane == 0) {
-      prev[(L - 1) & mask] = -2; prev[(L - 2) & mask] = -2; prev[(R + 1) & mask] = -2; prev[(R + 2) & mask] = -2;
+      prev[L - 1] = -2; prev[L - 2] = -2; prev[R + 1] = -2; prev[R + 2] = -2;
       C.row_left[e] = Lu; C.row_off[e] = aoff;
     }
     __syncwarp();
 
-    int term_d = 0x7fffffff, term_row = 0;
-    //  band pruning and best-cell bookkeeping are folded into the cell loop (forward.C:245-299): a cell survives
-    //  the pruning iff EA[e][d] + max(d,0) >= Edit_Match_Limit[e]; the new band is [min, max] surviving d, and the
-    //  longest cell of that band is always a surviving one (a pruned cell inside the band is shorter than the
-    //  nearest survivor on its left), so one pass over the row gives Left, Right, Longest and Best_d.
-    const int lim_e = P.eml[e];
-    int mn = 0x7fffffff, mx = -0x7fffffff, bv = -1, bd = 0x7fffffff;
-    for (uint32_t g = 0; g < ngroups; g++) {
-      const int d = Lu + (int)(g << 5) + lane;
-      const bool act = d <= Ru;
-      int row = 0, code = 0, lim = 0, cnt = 0;
-      bool more = false;
-      if (act) {
-        const uint32_t i0 = (uint32_t)(d - 1) & mask;
-        const int a = prev[i0], b = prev[(i0 + 1) & mask], c2 = prev[(i0 + 2) & mask];
-        row = 1 + b;
-        if (a > row) { row = a; code = 1; }
-        if (1 + c2 > row) { row = 1 + c2; code = 2; }
-        lim = min(m - row, n - d - row);
-        if (lim > 0) {
-          //  every lane slides its own diagonal over the first 8 bases (32-bit arithmetic) ...
-          cnt = ovl_match8(ovl_fetch8(A32, a0 + row), ovl_fetch8(T32, t0 + row + d));
-          more = (cnt == 8) && (lim > 8);
-          if (cnt > lim) cnt = lim;
-        }
-      }
-      //  ... and the few diagonals that are still matching (on real overlaps: the true one) are finished by the
-      //  whole warp, 512 bases per round, instead of one lane chasing dependent loads
-      for (unsigned pend = __ballot_sync(FULL, more); pend; pend &= pend - 1) {
-        const int l = __ffs(pend) - 1;
-        const int r_l = __shfl_sync(FULL, row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, lim, l);
-        const int ext = warp_slide(A, a0 + r_l + 8, T, t0 + r_l + d_l + 8, lim_l - 8, lane);
-        if (lane == l) cnt = 8 + ext;
-      }
-      if (act) {
-        row += cnt;
-        cur[d & mask] = row;
-        if (!(row + (d > 0 ? d : 0) < lim_e)) {
-          mn = min(mn, d); mx = max(mx, d);
-          if (row > bv) { bv = row; bd = d; }
-        }
-      }
-      unsigned b0 = __ballot_sync(FULL, act && (code & 1));
-      unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
-      if (lane == 0) C.arena[aoff + g] = make_uint2(b0, b1);
-      unsigned hb = __ballot_sync(FULL, act && (row == m || row + d == n));
-      if (hb) {
-        int tl = __ffs(hb) - 1;
-        term_d = Lu + (int)(g << 5) + tl;
-        term_row = __shfl_sync(FULL, row, tl);
-        break;
-      }
-    }
+    RowOut ro;
+    if (in_shared) dp_row_cells<true >(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
+    else           dp_row_cells<false>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
+    const int term_d = ro.term_d, term_row = ro.term_row;
+    int mn = ro.mn, mx = ro.mx; const int bv = ro.bv, bd = ro.bd;
     __syncwarp();
 
     if (term_d != 0x7fffffff) {
@@ -345,12 +377,12 @@ __device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uin
       }
       if (abort_) break;                                // best-so-far result, assembled after the loop
       int d = term_d;
-      if (fwd_rules && term_row == m && d < Ru && 1 + prev[(d + 1) & mask] == term_row) {
+      if (fwd_rules && term_row == m && d < Ru && 1 + prev[d + 1] == term_row) {
         //  Force the last error to be a mismatch (forward.C:215-221): the path now starts in cell (e, d+1), which
         //  the DP never evaluated (it may lie in a 32-cell group after the one that terminated), so its from-code
         //  is derived here from row e-1 exactly as Set_Right_Delta does (forward.C:45-55).
         d++;
-        const int pa = prev[(d - 1) & mask], pb = prev[d & mask], pc = prev[(d + 1) & mask];
+        const int pa = prev[d - 1], pb = prev[d], pc = prev[d + 1];
         int mx = 1 + pb; first_code = 0;
         if (pa > mx) { mx = pa; first_code = 1; }
         if (1 + pc > mx) first_code = 2;
@@ -378,7 +410,7 @@ __device__ __noinline__ void warp_dp(const uint64_t *A, int a0, int m, const uin
     double score = __dsub_rn(__dmul_rn((double)longest, P.bmv), (double)e);
     if (score > max_score) { max_score = score; ms_len = longest; ms_d = best_d; ms_e = best_e; }
 
-    int *t = prev; prev = cur; cur = t;
+    psel ^= 1; pbase = Lu;
     __syncwarp();
   }
 
@@ -411,36 +443,29 @@ __device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
 
   int rlen = 0, llen = 0;
   bool r_negate = false, l_negate = false;
+  s_hi = 0; t_hi = 0; s_lo = 0; t_lo = 0;
 
-  if (s_right_len == 0 || t_right_len == 0) {
-    s_hi = 0; t_hi = 0;
-  } else if (s_right_len <= t_right_len) {
-    warp_dp(C.s_fwd, s_right_begin, s_right_len, C.t_fwd, t_right_begin, t_right_len, error_limit, true, err_flags, lane);
+  //  side 0: forward(S + s_right_begin, T + t_right_begin); side 1: reverse(S + s_left_begin, T + t_left_begin), which is
+  //  the same forward code on the reverse complements starting at the mirrored position.  In both the shorter string plays
+  //  "A" (extend.C:86-121,129-162).  One loop, hence ONE call site of warp_dp: it is inlined without being duplicated.
+  #pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    const bool right = (side == 0);
+    const bool skip = right ? (s_right_len == 0 || t_right_len == 0) : (s_left_begin < 0 || t_left_begin < 0);
+    if (skip) continue;
+    const bool swap = right ? !(s_right_len <= t_right_len) : !(s_right_begin <= t_right_begin);     // T plays "A"
+    const uint64_t *sw = right ? C.s_fwd : C.s_rc, *tw = right ? C.t_fwd : C.t_rc;
+    const int s0 = right ? s_right_begin : S_len - 1 - s_left_begin, sl = right ? s_right_len : s_left_begin + 1;
+    const int t0 = right ? t_right_begin : T_len - 1 - t_left_begin, tl = right ? t_right_len : t_left_begin + 1;
+    warp_dp(swap ? tw : sw, swap ? t0 : s0, swap ? tl : sl, swap ? sw : tw, swap ? s0 : t0, swap ? sl : tl,
+            right ? error_limit : error_limit - right_errors, right, err_flags, lane);
     const DpOut o = C.o;
-    right_errors = o.errors; s_hi = o.a_end; t_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len; r_negate = true;
-  } else {
-    warp_dp(C.t_fwd, t_right_begin, t_right_len, C.s_fwd, s_right_begin, s_right_len, error_limit, true, err_flags, lane);
-    const DpOut o = C.o;
-    right_errors = o.errors; t_hi = o.a_end; s_hi = o.t_end; r_to_end = o.match_to_end; rlen = o.delta_len;
+    const int s_end = swap ? o.t_end : o.a_end, t_end = swap ? o.a_end : o.t_end;
+    if (right) { right_errors = o.errors; s_hi = s_end; t_hi = t_end; r_to_end = o.match_to_end; rlen = o.delta_len; r_negate = !swap; }
+    else       { left_errors = o.errors; s_lo = -s_end; t_lo = -t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover; l_negate = swap; }
   }
   s_hi += s_right_begin - 1;
   t_hi += t_right_begin - 1;
-
-  if (s_left_begin < 0 || t_left_begin < 0) {
-    s_lo = 0; t_lo = 0;
-  } else if (s_right_begin <= t_right_begin) {
-    //  reverse(S + s_left_begin, ...) == forward on the reverse complements, starting at the mirrored position
-    warp_dp(C.s_rc, S_len - 1 - s_left_begin, s_left_begin + 1, C.t_rc, T_len - 1 - t_left_begin, t_left_begin + 1,
-            error_limit - right_errors, false, err_flags, lane);
-    const DpOut o = C.o;
-    left_errors = o.errors; s_lo = -o.a_end; t_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
-  } else {
-    warp_dp(C.t_rc, T_len - 1 - t_left_begin, t_left_begin + 1, C.s_rc, S_len - 1 - s_left_begin, s_left_begin + 1,
-            error_limit - right_errors, false, err_flags, lane);
-    const DpOut o = C.o;
-    left_errors = o.errors; t_lo = -o.a_end; s_lo = -o.t_end; l_to_end = o.match_to_end; llen = o.delta_len; leftover = o.leftover;
-    l_negate = true;
-  }
   s_lo += s_left_begin + 1;
   t_lo += t_left_begin + 1;
   errors = left_errors + right_errors;
