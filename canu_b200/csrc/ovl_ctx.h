@@ -29,23 +29,30 @@ struct DevReads {
   size_t    cap_words = 0, cap_reads = 0, cap_groups = 0;
 };
 
-//  The k-mer index over the hash block: one 32-byte slot (= one DRAM sector) per DISTINCT k-mer in an
-//  open-addressed table (linear probing, load <= 0.5), pointing at the k-mer's occurrences in `occ`.
-//  The occurrences of a k-mer are contiguous and ordered by the class of the base that PRECEDES the
-//  occurrence in its hash read (0 = none: read start or N; 1..4 = A,C,G,T): class c is
-//  occ[c ? end[c-1] : start, end[c]).  Bit 63 of `key` marks a skip k-mer (the reference's Empty flag).
+//  The k-mer index over the hash block: one 32-byte slot (= one DRAM sector) per DISTINCT k-mer, the slots stored in
+//  PATH ORDER (by the position of the k-mer's first occurrence in the hash block) so that the consecutive windows of
+//  a read mostly fall into consecutive slots, plus an open-addressed hash table k-mer -> slot index (16-byte entries,
+//  load <= 0.5) for the places where the path breaks.  A slot points at the k-mer's occurrences in `occ`:
+//  contiguous, and ordered by the class of the base that PRECEDES the occurrence in its hash read (0 = none: read
+//  start or N; 1..4 = A,C,G,T): class c is occ[c ? end[c-1] : start, end[c]).  Bit 63 of `key` marks a skip k-mer
+//  (the reference's Empty flag).
 #define OVL_SKIP_BIT (1ull << 63)
 struct __align__(32) IndexSlot { uint64_t key; uint32_t start; uint32_t end[5]; };
+struct __align__(16) HashEntry { uint64_t key; uint32_t idx; uint32_t pad; };
 
 struct DevIndex {
-  uint64_t   cap = 0;             // slots in use
-  IndexSlot *slots = nullptr;     // [cap]
+  uint32_t   n_slots = 0;         // slots in use: distinct k-mers + skip k-mers no hash read holds
+  IndexSlot *slots = nullptr;     // [n_slots] path order
+  HashEntry *htab = nullptr;      // [hcap]
+  uint64_t   hcap = 0;
   uint32_t  *occ = nullptr;       // [n_occ] hash position index of each occurrence, sorted by (k-mer, class)
   uint64_t   n_occ = 0, n_distinct = 0;
   bool       built = false;
   uint64_t  *tkey = nullptr, *tkey2 = nullptr;   // build scratch: (k-mer << 3 | class) before / after the sort
   uint32_t  *tval = nullptr;                     // build scratch: position index before the sort
-  size_t     slots_cap = 0, occ_cap = 0, tkey_cap = 0, tkey2_cap = 0, tval_cap = 0;
+  IndexSlot *tmp_slots = nullptr;                // build scratch: slots in discovery order
+  uint32_t  *gk = nullptr, *gv = nullptr, *gk2 = nullptr, *gv2 = nullptr;   // build scratch: (first position, slot) before / after the path sort
+  size_t     slots_cap = 0, htab_cap = 0, occ_cap = 0, tkey_cap = 0, tkey2_cap = 0, tval_cap = 0, tmp_cap = 0, gk_cap = 0, gv_cap = 0, gk2_cap = 0, gv2_cap = 0;
 };
 
 struct DevCounters {              // mirrors ovlb_counters; device-resident, atomically updated

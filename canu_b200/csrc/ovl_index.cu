@@ -15,6 +15,7 @@
 #include "ovl_ctx.h"
 
 #include <cub/cub.cuh>
+#include <algorithm>
 
 #define WARPS_PER_BLOCK 8
 #define THREADS (WARPS_PER_BLOCK * 32)
@@ -205,70 +206,127 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
   return lo;
 }
 
-//  home slot: multiplicative (Fibonacci) hash, then scaled to [0, cap) -- every key bit reaches the top bits
-__device__ __forceinline__ uint64_t slot_home(uint64_t key, uint64_t cap) { return __umul64hi(key * 0x9E3779B97F4A7C15ull, cap); }
+//  ------------------------------------------------------------------------------------------------
+//  The index proper: PATH-ORDERED slots + a small hash table that finds a k-mer's slot.
+//
+//  One 32-byte IndexSlot per distinct k-mer, stored in the order in which the k-mers first occur in the hash block
+//  (position of the first occurrence, ascending).  Consecutive windows of a read therefore sit in consecutive slots
+//  wherever that read -- or any read covering the same stretch without an error -- was the first to bring those
+//  k-mers in, so the lookup of 32 consecutive ref windows is normally ONE 1 KB coalesced load (8 lines) instead of
+//  32 random probes that cost a 128-byte line each (tools/micro/rand_sector.cu: 36.9 G random lines/s is all B200
+//  gives, whatever the load width).  `htab` (open addressing, 16-byte entries: k-mer, slot index) is only consulted
+//  where the path breaks: a read start, an error, the border between two first-coverage stretches.
+//  ------------------------------------------------------------------------------------------------
+#define HT_EMPTY   0xFFFFFFFFFFFFFFFFull
+#define HT_NOTFOUND 0xFFFFFFFFu
 
-//  i-th slot of the probe sequence that starts at home slot h0.  A random access costs a whole 128-byte line on
-//  B200 (tools/micro/rand_sector.cu: 4 sectors of DRAM traffic per 32-byte load), so the sequence first cycles
-//  through the four slots of the home line and only then moves to the next line.  `cap` is a multiple of 4.
-__device__ __forceinline__ uint64_t probe_slot(uint64_t h0, uint32_t i, uint64_t cap) {
-  uint64_t b = (h0 >> 2) + (i >> 2);
-  const uint64_t nb = cap >> 2;
+__device__ __forceinline__ uint64_t ht_home(uint64_t key, uint64_t hcap) { return __umul64hi(key * 0x9E3779B97F4A7C15ull, hcap); }
+
+//  i-th entry of the probe sequence that starts at h0: first the eight entries of the home 128-byte line, then the
+//  next line.  `hcap` is a multiple of 8.
+__device__ __forceinline__ uint64_t ht_probe(uint64_t h0, uint32_t i, uint64_t hcap) {
+  uint64_t b = (h0 >> 3) + (i >> 3);
+  const uint64_t nb = hcap >> 3;
   if (b >= nb) b -= nb;
-  return (b << 2) | ((h0 + i) & 3);
+  return (b << 3) | ((h0 + i) & 7);
 }
 
-//  find the slot of `key`, inserting it if absent; returns the slot index
-__device__ __forceinline__ uint64_t slot_find_or_insert(IndexSlot *slots, uint64_t cap, uint64_t key) {
-  const uint64_t h0 = slot_home(key, cap);
+__device__ __forceinline__ uint32_t ht_find(const HashEntry *__restrict__ ht, uint64_t hcap, uint64_t key) {
+  const uint64_t h0 = ht_home(key, hcap);
   for (uint32_t i = 0;; i++) {
-    const uint64_t h = probe_slot(h0, i, cap);
-    unsigned long long *kp = (unsigned long long *)&slots[h].key;
-    unsigned long long k = *(volatile unsigned long long *)kp;
-    if ((k & ~OVL_SKIP_BIT) == key && k != OVL_EMPTY_KEY) return h;
-    if (k == OVL_EMPTY_KEY) {
-      unsigned long long old = atomicCAS(kp, (unsigned long long)OVL_EMPTY_KEY, (unsigned long long)key);
-      if (old == OVL_EMPTY_KEY || ((old & ~OVL_SKIP_BIT) == key)) return h;
+    const uint64_t h = ht_probe(h0, i, hcap);
+    uint64_t k, v;
+    asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(k), "=l"(v) : "l"(ht + h));
+    if (k == key) return (uint32_t)v;
+    if (k == HT_EMPTY) return HT_NOTFOUND;
+  }
+}
+
+//  claims an entry for `key` (which must not be in the table yet, or be inserted by nobody else concurrently)
+__device__ __forceinline__ void ht_insert(HashEntry *ht, uint64_t hcap, uint64_t key, uint32_t idx) {
+  const uint64_t h0 = ht_home(key, hcap);
+  for (uint32_t i = 0;; i++) {
+    const uint64_t h = ht_probe(h0, i, hcap);
+    unsigned long long *kp = (unsigned long long *)&ht[h].key;
+    if (*(volatile unsigned long long *)kp != HT_EMPTY) continue;
+    if (atomicCAS(kp, (unsigned long long)HT_EMPTY, (unsigned long long)key) == HT_EMPTY) { ht[h].idx = idx; return; }
+  }
+}
+
+//  one thread per sorted tuple; the first tuple of every k-mer emits the k-mer's slot (unordered, compacted) together
+//  with the position of the k-mer's first occurrence, the key of the path order
+__global__ void __launch_bounds__(256)
+k_group_heads(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ occ, uint32_t n_occ,
+              IndexSlot *__restrict__ tmp, uint32_t *__restrict__ gk, uint32_t *__restrict__ gv, unsigned long long *counter) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool head = false;
+  uint64_t k = 0;
+  if (i < n_occ) {
+    k = skey[i];
+    head = (i == 0) || ((skey[i - 1] >> 3) != (k >> 3));
+  }
+  uint32_t e[5]; uint32_t minpos = 0xFFFFFFFFu;
+  if (head) {
+    const uint64_t kmer = k >> 3;
+    uint32_t lo = (uint32_t)i;
+    #pragma unroll
+    for (int c = 0; c < 5; c++) {
+      const uint32_t nx = gallop_lower_bound(skey, lo, n_occ, (kmer << 3) + (uint64_t)(c + 1));
+      if (nx > lo) { const uint32_t p = occ[lo]; if (p < minpos) minpos = p; }      // occurrences of a class are in position order
+      lo = nx; e[c] = nx;
     }
   }
-}
-
-//  one thread per sorted tuple; the first tuple of every k-mer builds the k-mer's slot
-__global__ void __launch_bounds__(256)
-k_build_slots(const uint64_t *__restrict__ skey, uint32_t n_occ, IndexSlot *slots, uint64_t cap) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_occ) return;
-  const uint64_t k = skey[i];
-  if (i > 0 && (skey[i - 1] >> 3) == (k >> 3)) return;
-  const uint64_t kmer = k >> 3;
-  uint32_t e[5];
-  uint32_t lo = (uint32_t)i;
-  #pragma unroll
-  for (int c = 0; c < 5; c++) {
-    lo = gallop_lower_bound(skey, lo, n_occ, (kmer << 3) + (uint64_t)(c + 1));
-    e[c] = lo;
+  const unsigned m = __ballot_sync(0xffffffffu, head);
+  if (!m) return;
+  unsigned long long base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (head) {
+    const uint32_t c = (uint32_t)base + __popc(m & ((1u << lane) - 1));
+    uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
+    const uint64_t kmer = k >> 3;
+    sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), (uint32_t)i, e[0]);
+    sp[1] = make_uint4(e[1], e[2], e[3], e[4]);
+    gk[c] = minpos; gv[c] = c;
   }
-  const uint64_t h = slot_find_or_insert(slots, cap, kmer);
-  uint4 *sp = reinterpret_cast<uint4 *>(&slots[h]);
-  //  the key half was written by the CAS; fill in the rest (no other thread writes this slot)
-  slots[h].start = (uint32_t)i;
-  slots[h].end[0] = e[0];
-  sp[1] = make_uint4(e[1], e[2], e[3], e[4]);
 }
 
-//  one thread per skip k-mer: flag the slot (insert it if absent, Add_Extra_Hash_String) and mark screened read ends
-__global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip, int K, IndexSlot *slots, uint64_t cap,
+//  one thread per path position: gather the slot into place and publish it in the hash table
+__global__ void __launch_bounds__(256)
+k_path_slots(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ order, uint32_t n, IndexSlot *__restrict__ slots,
+             HashEntry *ht, uint64_t hcap) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint4 *src = reinterpret_cast<const uint4 *>(&tmp[order[j]]);
+  const uint4 a = src[0], b = src[1];
+  uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
+  dst[0] = a; dst[1] = b;
+  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j);
+}
+
+//  one thread per skip k-mer (the host passes each k-mer once): flag its slot, or append a flagged slot with an empty
+//  occurrence list if no hash read holds it (Add_Extra_Hash_String), and mark screened read ends
+__global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip, int K, IndexSlot *slots, uint32_t n_distinct,
+                             HashEntry *ht, uint64_t hcap, unsigned long long *n_extra,
                              const uint32_t *__restrict__ occ, const uint64_t *__restrict__ hpbase,
                              const uint32_t *__restrict__ hgrp_read, const uint32_t *__restrict__ hlen, uint32_t *hflags) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_skip) return;
   const uint64_t key = skip[i];
-  const uint64_t h = slot_find_or_insert(slots, cap, key);
-  const unsigned long long old = atomicOr((unsigned long long *)&slots[h].key, (unsigned long long)OVL_SKIP_BIT);
-  if (old & OVL_SKIP_BIT) return;                        // duplicate in the skip list: already handled
-  //  a slot inserted just now by this kernel has start/end still 0xFFFFFFFF: an absent k-mer, empty list
-  const uint32_t st = slots[h].start, en = slots[h].end[4];
-  if (st == 0xFFFFFFFFu) { slots[h].start = 0; slots[h].end[0] = 0; reinterpret_cast<uint4 *>(&slots[h])[1] = make_uint4(0, 0, 0, 0); return; }
+  const uint32_t idx = ht_find(ht, hcap, key);
+  if (idx == HT_NOTFOUND) {
+    const uint32_t j = n_distinct + (uint32_t)atomicAdd(n_extra, 1ull);
+    uint4 *sp = reinterpret_cast<uint4 *>(&slots[j]);
+    const uint64_t kk = key | OVL_SKIP_BIT;
+    sp[0] = make_uint4((uint32_t)kk, (uint32_t)(kk >> 32), 0, 0);
+    sp[1] = make_uint4(0, 0, 0, 0);
+    ht_insert(ht, hcap, key, j);
+    return;
+  }
+  atomicOr((unsigned long long *)&slots[idx].key, (unsigned long long)OVL_SKIP_BIT);
+  const uint32_t st = slots[idx].start, en = slots[idx].end[4];
   for (uint32_t j = st; j < en; j++) {                   // Mark_Screened_Ends_Chain (Build_Hash_Index.C:98-121)
     const uint32_t pos = occ[j];
     const uint32_t r = hgrp_read[pos >> 5];
@@ -292,22 +350,24 @@ __global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip,
 // ------------------------------------------------------------------------------------------------
 struct SlotView { bool found, skip; uint32_t start, e0, e1, e2, e3, e4; };
 
-__device__ __forceinline__ SlotView slot_lookup(const IndexSlot *__restrict__ slots, uint64_t cap, uint64_t key) {
-  SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
-  const uint64_t h0 = slot_home(key, cap);
-  for (uint32_t i = 0;; i++) {
-    const uint64_t h = probe_slot(h0, i, cap);
-    //  one 256-bit load = the whole slot = one 32-byte sector (LDG.E.256 on sm_100)
-    uint64_t k, q1, q2, q3;
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slots + h));
-    if (k == OVL_EMPTY_KEY) return v;
-    if ((k & ~OVL_SKIP_BIT) == key) {
-      v.found = true; v.skip = (k & OVL_SKIP_BIT) != 0;
-      v.start = (uint32_t)q1; v.e0 = (uint32_t)(q1 >> 32); v.e1 = (uint32_t)q2; v.e2 = (uint32_t)(q2 >> 32);
-      v.e3 = (uint32_t)q3; v.e4 = (uint32_t)(q3 >> 32);
-      return v;
-    }
-  }
+//  the slot at path index `idx` if it holds `key`
+__device__ __forceinline__ bool slot_at(const IndexSlot *__restrict__ slots, uint32_t idx, uint64_t key, SlotView &v) {
+  //  one 256-bit load = the whole slot = one 32-byte sector (LDG.E.256 on sm_100)
+  uint64_t k, q1, q2, q3;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(slots + idx));
+  if ((k & ~OVL_SKIP_BIT) != key) return false;
+  v.found = true; v.skip = (k & OVL_SKIP_BIT) != 0;
+  v.start = (uint32_t)q1; v.e0 = (uint32_t)(q1 >> 32); v.e1 = (uint32_t)q2; v.e2 = (uint32_t)(q2 >> 32);
+  v.e3 = (uint32_t)q3; v.e4 = (uint32_t)(q3 >> 32);
+  return true;
+}
+
+//  full lookup through the hash table; returns the path index or HT_NOTFOUND
+__device__ __forceinline__ uint32_t slot_lookup(const IndexSlot *__restrict__ slots, const HashEntry *__restrict__ ht, uint64_t hcap,
+                                                uint64_t key, SlotView &v) {
+  const uint32_t idx = ht_find(ht, hcap, key);
+  if (idx != HT_NOTFOUND) slot_at(slots, idx, key, v);
+  return idx;
 }
 
 #define SMALL_ITEM_MAX 8u
@@ -341,10 +401,17 @@ __device__ __forceinline__ void stage_append(ItemStage &S, bool has, uint4 item,
 }
 
 //  Persistent kernel: each warp walks PROBE_CHUNK consecutive groups at a time.
+//
+//  Lookup of the 32 windows of a group: lane l first tries path slot base + l, where `base` continues the slot of
+//  the previous group's last window (or comes from a hash-table lookup by the first lane still unresolved); every
+//  lane whose k-mer is there is done.  After PROBE_ROUNDS such rounds the lanes still unresolved (windows with read
+//  errors, path breaks) look themselves up through the hash table, in parallel.
+#define PROBE_ROUNDS 3
 __global__ void __launch_bounds__(THREADS)
 k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, const uint64_t *__restrict__ woff,
             const uint32_t *__restrict__ len, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
-            uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint64_t cap,
+            uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint32_t n_slots,
+            const HashEntry *__restrict__ ht, uint64_t hcap,
             uint32_t *__restrict__ ref_valid, uint32_t *rflags,
             uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work) {
   __shared__ uint4 stage[WARPS_PER_BLOCK][STAGE_SMALL + STAGE_LARGE];
@@ -359,6 +426,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
   for (uint64_t ch = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib; ch < n_chunks; ch += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
     const uint64_t gg_end = min(total, (ch + 1) * PROBE_CHUNK);
     uint32_t prev_r = 0xFFFFFFFFu; int prev_dir = -1; unsigned prev_top = 0;
+    uint32_t next_idx = HT_NOTFOUND;                          // path slot expected for window p0 if the path continues
     for (uint64_t gg = ch * PROBE_CHUNK; gg < gg_end; gg++) {
       const int dir = gg >= n_groups;
       const uint64_t g = dir ? gg - n_groups : gg;
@@ -367,11 +435,36 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       const int p0 = (int)(g * 32 - pbase[r]);
       const int p = p0 + lane;
       const uint64_t *w = (dir ? rc : fwd) + woff[r];
+      const bool carried = (r == prev_r && dir == prev_dir);    // the previous iteration was window group p0-32 of this read
 
       uint64_t key; int cls;
       const bool ok = warp_kmers(w, p0, L, K, lane, key, cls);
       SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
-      if (ok) v = slot_lookup(slots, cap, key);
+      uint32_t my_idx = HT_NOTFOUND;
+      {
+        unsigned need = __ballot_sync(0xffffffffu, ok);
+        uint32_t base = carried ? next_idx : HT_NOTFOUND;
+        for (int round = 0; need && round < PROBE_ROUNDS; round++) {
+          const int j = __ffs(need) - 1;
+          if (base == HT_NOTFOUND) {                            // lane j finds its own slot; the others follow it
+            uint32_t ij = HT_NOTFOUND;
+            if (lane == j) { ij = slot_lookup(slots, ht, hcap, key, v); my_idx = ij; }
+            ij = __shfl_sync(0xffffffffu, ij, j);
+            need &= ~(1u << j);
+            if (ij == HT_NOTFOUND || !need) continue;
+            base = ij - (uint32_t)j;
+          }
+          const uint32_t cand = base + (uint32_t)lane;
+          bool hit = false;
+          if (((need >> lane) & 1u) && cand < n_slots) hit = slot_at(slots, cand, key, v);
+          if (hit) my_idx = cand;
+          need &= ~__ballot_sync(0xffffffffu, hit);
+          base = HT_NOTFOUND;
+        }
+        if ((need >> lane) & 1u) my_idx = slot_lookup(slots, ht, hcap, key, v);
+        const uint32_t last = __shfl_sync(0xffffffffu, my_idx, 31);
+        next_idx = (last == HT_NOTFOUND) ? HT_NOTFOUND : last + 1;
+      }
       if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
         uint32_t f = 0;
         if (p == 0) f = 1u;
@@ -384,7 +477,6 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       const bool valid = v.found && !v.skip && v.e4 > v.start;
       const unsigned vm = __ballot_sync(0xffffffffu, valid);
       if (lane == 0) ref_valid[((uint64_t)dir * n_pos >> 5) + g] = vm;
-      const bool carried = (r == prev_r && dir == prev_dir);    // the previous iteration was window group p0-32 of this read
       const unsigned carry_top = prev_top;
       prev_r = r; prev_dir = dir; prev_top = vm >> 31;
       if (vm == 0) continue;
@@ -396,7 +488,8 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
         //  k-mer of window p0-1 = my k-mer shifted up one base with ref[p0-1] in front (it cannot contain an N:
         //  its last K-1 bases are mine and cls != 0 says base p0-1 is ACGT)
         const uint64_t pk = ((key << 2) | (uint64_t)(cls - 1)) & ((1ull << (2 * K)) - 1);
-        const SlotView pv = slot_lookup(slots, cap, pk);
+        SlotView pv; pv.found = false; pv.skip = false; pv.start = pv.e4 = 0;
+        slot_lookup(slots, ht, hcap, pk, pv);
         prev_valid = pv.found && !pv.skip && pv.e4 > pv.start;
       }
 
@@ -810,16 +903,34 @@ int ovl_build_index(ovlb_ctx *c) {
   X.n_distinct = h2[0];
   X.n_occ = h2[1];
 
-  //  one 32-byte slot per distinct k-mer (and per skip k-mer); load factor 1/3 (1.25 probes per hit, 1.6 per
-  //  miss) when that fits a sixth of the memory budget, else 1/2
-  uint64_t cap = 3 * (X.n_distinct + c->skip_keys.size()) + 64;
-  if (cap * sizeof(IndexSlot) > c->mem_budget / 6) cap = 2 * (X.n_distinct + c->skip_keys.size()) + 64;
-  cap = (cap + 3) & ~3ull;                              // whole 128-byte lines of four slots
-  if ((rc = ensure(X.slots, X.slots_cap, (size_t)cap, 9, 8))) return rc;
-  X.cap = cap;
-  CK(cudaMemsetAsync(X.slots, 0xFF, cap * sizeof(IndexSlot), c->stream));
+  //  slots in discovery order + the key of the path order (first position), then the path sort and the gather
+  std::vector<uint64_t> skip(c->skip_keys);
+  std::sort(skip.begin(), skip.end());
+  skip.erase(std::unique(skip.begin(), skip.end()), skip.end());
+  const uint64_t nd = X.n_distinct, ns = nd + skip.size();
+  if (ns >= 0xFFFFFFF0ull) { ovl_set_error("too many distinct k-mers for one index (>= 2^32); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
+  uint64_t hcap = ((2 * ns + 64) + 7) & ~7ull;            // whole 128-byte lines of eight entries, load <= 0.5
+  if ((rc = ensure(X.slots, X.slots_cap, (size_t)ns + 1, 9, 8))) return rc;
+  if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if ((rc = ensure(X.htab, X.htab_cap, (size_t)hcap, 9, 8))) return rc;
+  if ((rc = ensure(X.gk, X.gk_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if ((rc = ensure(X.gv, X.gv_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if ((rc = ensure(X.gk2, X.gk2_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if ((rc = ensure(X.gv2, X.gv2_cap, (size_t)nd + 1, 9, 8))) return rc;
+  X.hcap = hcap; X.n_slots = (uint32_t)nd;
+  CK(cudaMemsetAsync(X.htab, 0xFF, hcap * sizeof(HashEntry), c->stream));
+  CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
   if (X.n_occ) {
-    k_build_slots<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, (uint32_t)X.n_occ, X.slots, cap);
+    k_group_heads<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, X.occ, (uint32_t)X.n_occ, X.tmp_slots, X.gk, X.gv, &c->d_work[5]);
+    c->launches++;
+    int end_bit = 1; while (end_bit < 32 && (H.n_pos >> end_bit)) end_bit++;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, X.gk, X.gk2, X.gv, X.gv2, (int64_t)nd, 0, end_bit, c->stream);
+    if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
+    size_t tb2 = c->cub_temp_cap;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.gk, X.gk2, X.gv, X.gv2, (int64_t)nd, 0, end_bit, c->stream));
+    c->launches += 2 + (end_bit + 7) / 8;
+    k_path_slots<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gv2, (uint32_t)nd, X.slots, X.htab, hcap);
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -827,15 +938,19 @@ int ovl_build_index(ovlb_ctx *c) {
   c->host_counters[CT_HASH_KMERS] += X.n_occ;
 
   EvTimer t4(c->stream);
-  if (!c->skip_keys.empty()) {
+  if (!skip.empty()) {
     uint64_t *d_skip = nullptr;
-    CK(cudaMalloc((void **)&d_skip, c->skip_keys.size() * 8));
-    CK(cudaMemcpyAsync(d_skip, c->skip_keys.data(), c->skip_keys.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    k_index_skip<<<div_up(c->skip_keys.size(), 128), 128, 0, c->stream>>>(d_skip, c->skip_keys.size(), K, X.slots, cap, X.occ,
-                                                                          H.pbase, H.grp_read, H.len, H.flags);
+    CK(cudaMalloc((void **)&d_skip, skip.size() * 8));
+    CK(cudaMemcpyAsync(d_skip, skip.data(), skip.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(&c->d_work[5], 0, 8, c->stream));
+    k_index_skip<<<div_up(skip.size(), 128), 128, 0, c->stream>>>(d_skip, skip.size(), K, X.slots, (uint32_t)nd, X.htab, hcap, &c->d_work[5],
+                                                                  X.occ, H.pbase, H.grp_read, H.len, H.flags);
     c->launches++;
+    unsigned long long n_extra = 0;
+    CK(cudaMemcpyAsync(&n_extra, &c->d_work[5], 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(d_skip);
+    X.n_slots = (uint32_t)(nd + n_extra);
   }
   CK(cudaGetLastError());
   c->timings.index_skip_ms = t4.stop();
@@ -882,7 +997,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ref_probe, THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     k_ref_probe<<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
-        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.cap,
+        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.n_slots, X.htab, X.hcap,
         c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work);
     c->launches++;
   }
