@@ -128,6 +128,7 @@ struct ovlb_ctx {
   OvlRun   *runs_extra = nullptr; size_t runs_extra_cap = 0;
   uint64_t  n_runs = 0;
   uint32_t *pair_flag = nullptr, *pair_idx = nullptr;
+  const uint32_t *pair_order = nullptr;   // extension order of the pairs (heaviest first) or null = index order; aliases chain scratch
   void     *cub_temp = nullptr;   size_t cub_temp_cap = 0;
   PairRec  *pairs = nullptr;      uint64_t pair_cap = 0, n_pairs = 0;
   int32_t  *seed_start = nullptr, *seed_off = nullptr, *seed_len = nullptr;   // [n_runs] list order per pair

@@ -606,7 +606,7 @@ __device__ __forceinline__ void bind_warp_ctl(const DevParams &P, const ExtScrat
 //  Persistent kernel: warps pull pairs from a global cursor (pairs differ wildly in cost).
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(EXT_THREADS, MIN_BLOCKS)
-k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, uint64_t n_pairs,
+k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, const uint32_t *__restrict__ order, uint64_t n_pairs,
                const int32_t *__restrict__ seed_start, const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_len,
                uint8_t *seed_alive,
                const uint64_t *__restrict__ rfwd, const uint64_t *__restrict__ rrc, const uint64_t *__restrict__ rwoff,
@@ -627,7 +627,7 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, ui
     if (lane == 0) pi = atomicAdd(&work[1], 1ull);
     pi = __shfl_sync(FULL, pi, 0);
     if (pi >= n_pairs) break;
-    const PairRec pr = pairs[pi];
+    const PairRec pr = pairs[order ? (unsigned long long)order[pi] : pi];
     if (pr.n_seeds == 0) continue;
 
     __syncwarp();
@@ -855,7 +855,7 @@ int ovl_extend_pairs(ovlb_ctx *c) {
   if (!min_blocks) { const char *ev = getenv("OVLB_EXT_BLOCKS"); min_blocks = ev ? atoi(ev) : 4; if (min_blocks < 2 || min_blocks > 4) min_blocks = 4; }
   if ((uint64_t)c->sm_count * min_blocks < (uint64_t)blocks) blocks = c->sm_count * min_blocks;
 #define EXT_LAUNCH(MB) k_extend_pairs<MB><<<blocks, EXT_THREADS, smem, c->stream>>>( \
-      c->dp, c->ext, c->pairs, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \
+      c->dp, c->ext, c->pairs, c->pair_order, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \
       c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->ref.first_id, \
       c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len, c->hash.first_id, \
       c->d_records, c->rec_cap, c->d_work, c->d_counters->v)

@@ -757,6 +757,17 @@ k_chain_pairs(PairRec *pairs, uint64_t n_pairs, uint64_t n_runs, const OvlRun *_
   pairs[pi] = pr;
 }
 
+//  Scheduling key of a pair for the extension kernel: pairs with many seeds (non-consistent pairs on noisy reads: one
+//  Extend_Alignment per surviving seed) go first, so that the persistent kernel does not end on a few warps grinding
+//  through the heaviest pairs (longest-processing-time-first).  Ascending sort on ~cost.
+__global__ void k_pair_cost(const PairRec *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ key, uint32_t *__restrict__ val) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const PairRec pr = pairs[i];
+  const uint32_t cost = pr.n_seeds <= 0 ? 0u : (pr.consistent ? 1u : (uint32_t)pr.n_seeds);
+  key[i] = ~cost; val[i] = i;
+}
+
 // ------------------------------------------------------------------------------------------------
 //  host-side launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -1106,6 +1117,18 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
                                                          c->seed_start, c->seed_off, c->seed_len, c->seed_alive, c->dp,
                                                          R.len, R.flags, H.len, H.flags, c->d_counters->v);
   c->launches++;
+  c->pair_order = nullptr;
+  if (nr > 3 * np && np > 1 && np < 0xFFFFFFFFull) {      // many seeds per pair: noisy reads, pair costs differ by orders of magnitude
+    uint32_t *k1 = c->pair_flag, *v1 = c->pair_idx, *k2 = (uint32_t *)c->sim_nxt, *v2 = (uint32_t *)c->sim_hits;   // all free now, >= nr entries
+    k_pair_cost<<<div_up(np, 256), 256, 0, c->stream>>>(c->pairs, (uint32_t)np, k1, v1); c->launches++;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k1, k2, v1, v2, (int64_t)np, 0, 32, c->stream);
+    if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
+    size_t tb2 = c->cub_temp_cap;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, k1, k2, v1, v2, (int64_t)np, 0, 32, c->stream));
+    c->launches += 6;
+    c->pair_order = v2;
+  }
   CK(cudaGetLastError());
   c->timings.chain_ms = t4.stop();
   return OVLB_OK;
