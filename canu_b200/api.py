@@ -73,7 +73,7 @@ PAIR_DTYPE = np.dtype([("ref_id", "<u4"), ("hash_id", "<u4"), ("dir", "<i4"), ("
 SEED_DTYPE = np.dtype([("start", "<i4"), ("offset", "<i4"), ("len", "<i4")])
 
 EXPORTS = [
-    "ovlb_last_error", "ovlb_device_count", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
+    "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend",

@@ -34,6 +34,16 @@ int ovlb_device_count(void) {
   return n;
 }
 
+int ovlb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes) {
+  size_t f = 0, t = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) {
+    cudaGetLastError(); ovl_set_error("ovlb_device_memory: bad device or no CUDA"); return OVLB_ERR_CUDA;
+  }
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return OVLB_OK;
+}
+
 int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   if (!p || !out) { ovl_set_error("ovlb_create: null argument"); return OVLB_ERR_ARG; }
   *out = nullptr;

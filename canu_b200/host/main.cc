@@ -7,7 +7,8 @@
 //
 //  Flags that only size the reference's CPU data structures are accepted and ignored because the
 //  output does not depend on them: --hashbits, --hashload, --hashdatalen, -t.
-//  Extra flags of this build: --gpu N (device, default 0), --gpus a,b,..|all, --refbatch BASES, --hashblock BASES.
+//  Extra flags of this build: --gpu N (device, default 0), --gpus a,b,..|all, --streams N (contexts per device,
+//  default 1; measured: two contexts per B200 do NOT pay -- their persistent kernels serialise and the tiles get smaller), --refbatch BASES, --hashblock BASES.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -15,10 +16,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "../../include/ovlb200.h"
 #include "ovfile.h"
@@ -40,6 +43,8 @@ struct Options {
   int      gpu = 0;
   std::vector<int> gpus;           // --gpus a,b,..  (or "all")
   uint64_t refBatchBases = 0, hashBlockBases = 0;
+  int      streams = 1;            // --streams: worker contexts per device
+  std::vector<int> visibleRemap;   // physical device of each visible index when we set CUDA_VISIBLE_DEVICES ourselves
 };
 
 static bool file_exists(const char *p) { struct stat st; return stat(p, &st) == 0 && S_ISREG(st.st_mode); }
@@ -74,12 +79,13 @@ static void usage(const char *argv0) {
   fprintf(stderr, "--hashbits n / --hashdatalen n / --hashload f   accepted and ignored (output does not depend on them)\n\n");
   fprintf(stderr, "--gpu n            CUDA device to use (default 0)\n");
   fprintf(stderr, "--gpus a,b,..|all  spread the job's hash-block x ref-block tiles over several CUDA devices\n");
+  fprintf(stderr, "--streams n        worker contexts per device (default 1)\n");
   fprintf(stderr, "--refbatch n       bases of reference reads per device batch\n");
   fprintf(stderr, "--hashblock n      bases of hash reads per device-resident index\n\n");
 }
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-struct Phase { double create = 0, pack_hash = 0, index = 0, pack_ref = 0, stage = 0, run = 0, fetch = 0; };
+struct Phase { double create = 0, pack_hash = 0, index = 0, pack_ref = 0, stage = 0, run = 0, fetch = 0, submit = 0, destroy = 0, total = 0; };
 
 #define FAIL(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } while (0)
 
@@ -191,6 +197,7 @@ int main(int argc, char **argv) {
       if (!strcmp(v, "all")) G.gpus.push_back(-1);
       else for (const char *q = v; *q; ) { G.gpus.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q == ',') q++; }
     }
+    else if (!strcmp(a, "--streams"))     G.streams = std::max(1, std::min(4, atoi(need(a))));
     else if (!strcmp(a, "--refbatch"))    G.refBatchBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--hashblock"))   G.hashBlockBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--version"))     { printf("overlapInCore (canu_b200, B200-native ovl) for canu v2.3\n"); return 0; }
@@ -204,6 +211,28 @@ int main(int argc, char **argv) {
 
   auto t_start = std::chrono::steady_clock::now();
 
+  const double t_begin = now_s();
+  //  CUDA initialisation costs seconds on a multi-GPU node (the driver brings up every visible device), so (a) when the
+  //  devices are named explicitly only those are made visible, and (b) it runs on its own thread while the store is
+  //  opened and the host tables are built.
+  if (!G.gpus.empty() ? G.gpus[0] >= 0 : true) {
+    if (getenv("CUDA_VISIBLE_DEVICES") == nullptr) {
+      std::vector<int> want = G.gpus.empty() ? std::vector<int>{G.gpu} : G.gpus;
+      std::vector<int> uniq(want); std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+      bool sane = true; for (int d : uniq) if (d < 0 || d > 1023) sane = false;
+      if (sane) {
+        std::string vis;
+        for (size_t i = 0; i < uniq.size(); i++) { if (i) vis += ","; vis += std::to_string(uniq[i]); }
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+        for (int &d : want) d = (int)(std::lower_bound(uniq.begin(), uniq.end(), d) - uniq.begin());
+        G.gpus = want; G.gpu = want[0];
+        G.visibleRemap = uniq;
+      }
+    }
+  }
+  int ndev_async = 0;
+  std::thread cuda_init([&ndev_async] { ndev_async = ovlb_device_count(); });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } cuda_init_joiner{cuda_init};
   SqStore store;
   std::string e;
   if (!store.open(G.storePath, e)) FAIL("sqStore()--  failed to open '%s' for read-only access: %s.", G.storePath, e.c_str());
@@ -213,13 +242,7 @@ int main(int argc, char **argv) {
   if (G.bgnRefID < 1)  G.bgnRefID = 1;
   if (G.endRefID > N)  G.endRefID = N;
 
-  const int ndev = ovlb_device_count();
-  if (ndev == 0) FAIL("ERROR: no CUDA device found; this overlapInCore has no CPU path.");
-  if (G.gpus.empty()) G.gpus.push_back(G.gpu);
-  if (G.gpus.size() == 1 && G.gpus[0] < 0) { G.gpus.clear(); for (int d = 0; d < ndev; d++) G.gpus.push_back(d); }
-  for (int d : G.gpus) if (d < 0 || d >= ndev) FAIL("ERROR: --gpu/--gpus names device %d but only %d CUDA device(s) exist", d, ndev);
-  const uint32_t W = (uint32_t)G.gpus.size();
-
+  const double t_store = now_s();
   //  A read must be at least --minlength long to be hashed or searched, and at least K long to hold a k-mer.
   const uint32_t minLen = (uint32_t)std::max<int64_t>(G.minOlapLen, (int64_t)G.kmerLen);
   uint32_t maxLen = 64;
@@ -235,8 +258,37 @@ int main(int argc, char **argv) {
   if (ovlb_params_init(&P, (uint32_t)G.kmerLen, G.maxErate, G.alignNoise, G.partial, G.unique, G.minOlapLen, G.noHopeless, G.minKmers, maxLen))
     FAIL("ERROR: %s", ovlb_last_error());
 
+  const double t_params = now_s();
   std::vector<uint64_t> skip;
   if (G.kmerSkipFileName && load_skip_kmers(G.kmerSkipFileName, (uint32_t)G.kmerLen, skip)) return 1;
+
+  cuda_init.join();
+  const int ndev = ndev_async;
+  if (ndev == 0) FAIL("ERROR: no CUDA device found; this overlapInCore has no CPU path.");
+  if (!G.visibleRemap.empty() && (size_t)ndev < G.visibleRemap.size()) FAIL("ERROR: --gpu/--gpus names a CUDA device that does not exist (%d of the %zu named are visible)", ndev, G.visibleRemap.size());
+  if (G.gpus.empty()) G.gpus.push_back(G.gpu);
+  if (G.gpus.size() == 1 && G.gpus[0] < 0) { G.gpus.clear(); for (int d = 0; d < ndev; d++) G.gpus.push_back(d); }
+  for (int d : G.gpus) if (d < 0 || d >= ndev) FAIL("ERROR: --gpu/--gpus names device %d but only %d CUDA device(s) exist", d, ndev);
+  const double t_cuda = now_s();
+  //  --streams contexts per device, each with its own stream, buffers and share of the device's memory: while one
+  //  packs reads, copies records or sits in the tail of its extension kernel, the other's kernels fill the SMs.
+  //  (A device listed twice in --gpus already asks for that explicitly and is left alone.)
+  std::vector<int> sharers;                                             // contexts on the device of worker wi
+  {
+    std::vector<int> uniq(G.gpus); std::sort(uniq.begin(), uniq.end());
+    const bool listed_twice = std::adjacent_find(uniq.begin(), uniq.end()) != uniq.end();
+    const int per = listed_twice ? 1 : G.streams;
+    std::vector<int> all;
+    for (int d : G.gpus) for (int k = 0; k < per; k++) all.push_back(d);
+    G.gpus = all;
+    for (int d : G.gpus) sharers.push_back((int)std::count(G.gpus.begin(), G.gpus.end(), d));
+  }
+  //  free memory of a device, asked once (by the first worker that gets there, on its own thread: creating the
+  //  device's primary context is the slow part and must not be serialised over the devices)
+  std::vector<uint64_t> devFree(ndev, 0);
+  std::vector<std::mutex> devMu(ndev);
+  auto phys = [&G](int d) { return (size_t)d < G.visibleRemap.size() ? G.visibleRemap[d] : d; };
+  const uint32_t W = (uint32_t)G.gpus.size();
 
   OvFileWriter out;
   if (!out.open(G.outName, N, e)) FAIL("ERROR: %s", e.c_str());
@@ -245,7 +297,10 @@ int main(int argc, char **argv) {
   //  sized for HBM, ref batches sized for the device seed buffers -- and small enough that every GPU gets several.
   const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : 1500000000ull;
   uint64_t refBatch = G.refBatchBases ? G.refBatchBases : 256000000ull;
-  if (W > 1 && !G.refBatchBases) refBatch = std::max<uint64_t>(std::min<uint64_t>(refBatch, refBasesTotal / (4ull * W) + 1), 4000000ull);
+  //  Several workers: every one should get a few tiles of each hash block so that longest-first assignment can balance
+  //  them, but not many small ones -- an extension launch cannot end before its slowest pair does (0.2 - 1 s on noisy
+  //  reads, tools/scale_run.py), so a tile should hold tens of pairs per resident warp.
+  if (W > 1 && !G.refBatchBases) refBatch = std::max<uint64_t>(std::min<uint64_t>(refBatch, refBasesTotal / (2ull * W) + 1), 16000000ull);
 
   std::vector<ovlb_tile> tiles;
   {
@@ -277,8 +332,8 @@ int main(int argc, char **argv) {
     } else if (ovlb_assign_tiles(tiles.data(), tiles.size(), W, owner.data())) FAIL("ERROR: %s", ovlb_last_error());
   }
 
-  fprintf(stderr, "overlapInCore (B200): store '%s' has %u reads (version flags 0x%x); hash %u-%u ref %u-%u; %zu tile(s) on %u GPU(s)\n",
-          G.storePath, N, store.version(), G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID, tiles.size(), W);
+  fprintf(stderr, "overlapInCore (B200): store '%s' has %u reads (version flags 0x%x); hash %u-%u ref %u-%u; %zu tile(s) on %u context(s) of %zu GPU(s)\n",
+          G.storePath, N, store.version(), G.bgnHashID, G.endHashID, G.bgnRefID, G.endRefID, tiles.size(), W, std::set<int>(G.gpus.begin(), G.gpus.end()).size());
 
   //  One worker thread per GPU; tiles share nothing, records go to the one writer thread, counters are summed.
   std::vector<ovlb_counters> counters(W);
@@ -293,8 +348,16 @@ int main(int argc, char **argv) {
     if (!st.open(G.storePath, err)) { werr[wi] = err; return; }
     ovlb_ctx *ctx = nullptr;
     Phase &ph = phase[wi];
+    const double t_worker = now_s();
     double t0 = now_s();
-    if (ovlb_create(G.gpus[wi], &P, &ctx)) { werr[wi] = ovlb_last_error(); return; }
+    ovlb_params Pw = P;
+    {
+      const int d = G.gpus[wi];
+      std::lock_guard<std::mutex> lk(devMu[d]);
+      if (devFree[d] == 0) { uint64_t tot = 0; if (ovlb_device_memory(d, &devFree[d], &tot)) { werr[wi] = ovlb_last_error(); return; } }
+      Pw.device_mem_budget = (uint64_t)((double)devFree[d] * 0.8 / sharers[wi]);
+    }
+    if (ovlb_create(G.gpus[wi], &Pw, &ctx)) { werr[wi] = ovlb_last_error(); return; }
     ph.create += now_s() - t0;
     Packed HB, RB;
     uint32_t curHb = 0, curHe = 0;
@@ -307,7 +370,7 @@ int main(int argc, char **argv) {
         t0 = now_s();
         if (!pack_range(st, T.hash_bgn, T.hash_end, G.minLibToHash, G.maxLibToHash, minLen, HB, err)) { werr[wi] = err; break; }
         ph.pack_hash += now_s() - t0; t0 = now_s();
-        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Build_Hash_Index from %u to %u (%lu bases)\n", G.gpus[wi], T.hash_bgn, T.hash_end, (unsigned long)HB.bases); }
+        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Build_Hash_Index from %u to %u (%lu bases)\n", phys(G.gpus[wi]), T.hash_bgn, T.hash_end, (unsigned long)HB.bases); }
         if (ovlb_load_hash_reads(ctx, &HB.view) ||
             (!skip.empty() && ovlb_mark_skip_kmers(ctx, skip.data(), skip.size())) ||
             ovlb_build_index(ctx)) { werr[wi] = ovlb_last_error(); break; }
@@ -338,13 +401,18 @@ int main(int argc, char **argv) {
         recs.resize(n);
         if (ovlb_fetch_records(ctx, recs.data(), recs.size(), &n)) { werr[wi] = ovlb_last_error(); break; }
         ph.fetch += now_s() - t0;
-        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", G.gpus[wi], rb, r2, T.hash_bgn, T.hash_end, (unsigned long)RB.bases, (unsigned long)n); }
+        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", phys(G.gpus[wi]), rb, r2, T.hash_bgn, T.hash_end, (unsigned long)RB.bases, (unsigned long)n); }
+        t0 = now_s();
         out.submit(std::move(recs));
         recs = std::vector<ovlb_record>();
+        ph.submit += now_s() - t0;
       }
     }
     if (werr[wi].empty() && ovlb_get_counters(ctx, &counters[wi])) werr[wi] = ovlb_last_error();
+    t0 = now_s();
     ovlb_destroy(ctx);
+    ph.destroy += now_s() - t0;
+    ph.total = now_s() - t_worker;
   };
   if (W == 1) worker(0);
   else {
@@ -352,7 +420,7 @@ int main(int argc, char **argv) {
     for (uint32_t wi = 0; wi < W; wi++) th.emplace_back(worker, wi);
     for (auto &t : th) t.join();
   }
-  for (uint32_t wi = 0; wi < W; wi++) if (!werr[wi].empty()) FAIL("ERROR: [gpu %d] %s", G.gpus[wi], werr[wi].c_str());
+  for (uint32_t wi = 0; wi < W; wi++) if (!werr[wi].empty()) FAIL("ERROR: [gpu %d] %s", phys(G.gpus[wi]), werr[wi].c_str());
 
   ovlb_counters C;
   memset(&C, 0, sizeof(C));
@@ -365,11 +433,13 @@ int main(int argc, char **argv) {
   if (!out.close(e)) FAIL("ERROR: %s", e.c_str());
   ovlb_params_free(&P);
   const double t_closed = now_s();
-  fprintf(stderr, "phases (s): setup %.2f | workers %.2f | writer drain %.2f\n",
-          t_setup_done - std::chrono::duration<double>(t_start.time_since_epoch()).count(), t_workers_done - t_setup_done, t_closed - t_workers_done);
+  fprintf(stderr, "phases (s): setup %.2f (store %.2f, lengths+tables %.2f, wait for cuda init %.2f, plan+open %.2f) | workers %.2f | writer drain %.2f\n",
+          t_setup_done - t_begin, t_store - t_begin, t_params - t_store, t_cuda - t_params, t_setup_done - t_cuda,
+          t_workers_done - t_setup_done, t_closed - t_workers_done);
   for (uint32_t wi = 0; wi < W; wi++)
-    fprintf(stderr, "  [gpu %d] create %.2f  pack-hash %.2f  load+index %.2f  pack-ref %.2f  stage %.2f  run %.2f  fetch %.2f\n", G.gpus[wi],
-            phase[wi].create, phase[wi].pack_hash, phase[wi].index, phase[wi].pack_ref, phase[wi].stage, phase[wi].run, phase[wi].fetch);
+    fprintf(stderr, "  [gpu %d] create %.2f  pack-hash %.2f  load+index %.2f  pack-ref %.2f  stage %.2f  run %.2f  fetch %.2f  submit %.2f  destroy %.2f  (worker total %.2f)\n", phys(G.gpus[wi]),
+            phase[wi].create, phase[wi].pack_hash, phase[wi].index, phase[wi].pack_ref, phase[wi].stage, phase[wi].run, phase[wi].fetch,
+            phase[wi].submit, phase[wi].destroy, phase[wi].total);
 
   FILE *stats = stderr;
   if (G.statName) {
@@ -390,5 +460,7 @@ int main(int argc, char **argv) {
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
   fprintf(stderr, "%lu overlaps, %lu candidate pairs, %lu DP cells in %.2f s\nBye.\n",
           (unsigned long)out.numOverlaps(), (unsigned long)C.pairs, (unsigned long)C.dp_cells, secs);
-  return 0;
+  //  every output is closed; skip the CUDA runtime's process-exit teardown (hundreds of ms per device)
+  fflush(stdout); fflush(stderr);
+  _exit(0);
 }

@@ -135,6 +135,9 @@ typedef struct {
 
 const char *ovlb_last_error(void);
 int  ovlb_device_count(void);
+/*  Free and total HBM of a device, bytes (cudaMemGetInfo); lets a host that runs several contexts on one device
+ *  split the memory between them through ovlb_params.device_mem_budget.  */
+int  ovlb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 
 int  ovlb_create(int device, const ovlb_params *params, ovlb_ctx **out);
 void ovlb_destroy(ovlb_ctx *ctx);
