@@ -16,6 +16,7 @@
 
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <cstdlib>
 
 #define WARPS_PER_BLOCK 8
 #define THREADS (WARPS_PER_BLOCK * 32)
@@ -158,6 +159,193 @@ k_hash_tuples(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ wof
   const bool ok = warp_kmers(fwd + woff[r], p0, L, K, lane, key, cls);
   tkey[g * 32 + lane] = ok ? ((key << 3) | (uint64_t)cls) : (1ull << (2 * K + 3));     // invalid windows sort last
   tval[g * 32 + lane] = (uint32_t)(g * 32 + lane);
+}
+
+//  Tuples for the bucketed build: only the valid windows, compacted (one atomic per block), and the k-mer replaced
+//  by k-mer * mixc mod 4^K -- a bijection whose TOP bits depend on every base, so that the top bits of the key cut the
+//  tuples into even buckets whatever the base composition of the reads.
+__global__ void __launch_bounds__(THREADS)
+k_hash_tuples_compact(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
+                      const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read, uint64_t n_groups,
+                      int K, uint64_t mixc, uint64_t *__restrict__ tkey, uint32_t *__restrict__ tval, unsigned long long *counter) {
+  __shared__ unsigned int wcnt[WARPS_PER_BLOCK];
+  __shared__ unsigned long long blk_base;
+  const uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t key = 0; int cls = 0; bool ok = false;
+  if (g < n_groups) {
+    const uint32_t r = grp_read[g];
+    ok = warp_kmers(fwd + woff[r], (int)(g * 32 - pbase[r]), (int)len[r], K, lane, key, cls);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) wcnt[wid] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tot = 0;
+    #pragma unroll
+    for (int w = 0; w < WARPS_PER_BLOCK; w++) { const unsigned int t = wcnt[w]; wcnt[w] = tot; tot += t; }
+    blk_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (ok) {
+    const uint64_t i = blk_base + wcnt[wid] + __popc(m & ((1u << lane) - 1));
+    tkey[i] = (((key * mixc) & ((1ull << (2 * K)) - 1)) << 3) | (uint64_t)cls;
+    tval[i] = (uint32_t)(g * 32 + lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Bucketed index build.  After ceil(B/8) radix passes over the top B bits of the (mixed) tuple keys the tuples of a
+//  bucket are contiguous (a few thousand: BK_TARGET on average).  One CTA then finishes a bucket entirely in shared
+//  memory: a hash table gives every distinct k-mer of the bucket a slot and counts its occurrences per class of the
+//  preceding base, a prefix sum turns the counts into offsets, and the positions are scattered to their
+//  (k-mer, class) segment.  That is everything the index needs -- the order of the k-mers inside a bucket and of the
+//  positions inside a class is immaterial -- so the remaining radix passes, the distinct count and the
+//  class-boundary searches of the sorted build (k_count_distinct, k_group_heads) are not run at all.
+// ------------------------------------------------------------------------------------------------
+#define BK_THREADS 1024
+#define BK_PER     (BK_CAP / BK_THREADS)     // tuples per thread, staged in registers
+#define BK_CAP     6144                 // tuples of a bucket that fit shared memory
+#define BK_TARGET  4096                 // mean bucket size the bucket count is chosen for
+#define BK_TABLE   4096                 // hash-table entries per bucket
+#define BK_MAXDIST 3584                 // distinct k-mers a bucket may hold (load 0.875)
+#define BK_SMEM    (BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 8 + BK_TABLE * 5 * 4 + 64)
+
+//  first tuple of every bucket (bucket = key >> shift) in the partitioned tuple array; offs[nb] = n
+__global__ void k_bucket_offsets(const uint64_t *__restrict__ key, uint64_t n, int shift, uint32_t nb, uint32_t *__restrict__ offs) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  if (b == nb) { offs[b] = (uint32_t)n; return; }
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((key[mid] >> shift) < b) lo = mid + 1; else hi = mid; }
+  offs[b] = (uint32_t)lo;
+}
+
+//  out[0]: distinct k-mers (slot records emitted), out[1]: bit 0 = a bucket did not fit (caller falls back to the
+//  sorted build)
+__global__ void __launch_bounds__(BK_THREADS, 1)
+k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ offs, uint32_t nb,
+               int K, uint64_t mix_inv, uint32_t *__restrict__ occ, IndexSlot *__restrict__ tmp, uint32_t tmp_cap,
+               uint32_t *__restrict__ gk, uint32_t *__restrict__ gv, unsigned long long *out) {
+  extern __shared__ __align__(16) unsigned char bk_sm[];
+  uint64_t *tk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_CAP] mixed k-mer of each tuple; later: uint32 positions, grouped
+  uint32_t *tp = reinterpret_cast<uint32_t *>(tk + BK_CAP);              // [BK_CAP] position of each tuple
+  uint16_t *ts = reinterpret_cast<uint16_t *>(tp + BK_CAP);              // [BK_CAP] slot << 3 | class
+  uint64_t *hk = reinterpret_cast<uint64_t *>(ts + BK_CAP);              // [BK_TABLE] mixed k-mer of the slot
+  uint32_t *hc = reinterpret_cast<uint32_t *>(hk + BK_TABLE);            // [BK_TABLE * 5] count -> start -> end of (slot, class)
+  __shared__ unsigned int n_dist, bad, slot_base;
+  __shared__ unsigned int wsum[BK_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  uint32_t *gpos = reinterpret_cast<uint32_t *>(tk);
+
+  for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+    const uint32_t s0 = offs[b], m = offs[b + 1] - s0;
+    if (m == 0) continue;
+    if (m > BK_CAP) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
+    __syncthreads();                                                     // previous bucket fully written out
+    for (int i = tid; i < BK_TABLE; i += BK_THREADS) hk[i] = ~0ull;
+    for (int i = tid; i < BK_TABLE * 5; i += BK_THREADS) hc[i] = 0;
+    if (tid == 0) { n_dist = 0; bad = 0; }
+    __syncthreads();
+    //  load (all of a thread's tuples in flight at once), find/insert the k-mer, count per (slot, class)
+    uint64_t kreg[BK_PER]; uint32_t preg[BK_PER];
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      kreg[j] = i < m ? pkey[s0 + i] : 0ull;
+      preg[j] = i < m ? ppos[s0 + i] : 0u;
+    }
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      if (i >= m) break;
+      const uint64_t t = kreg[j];
+      tp[i] = preg[j];
+      const uint32_t cls = (uint32_t)t & 7u;
+      const uint64_t km = t >> 3;
+      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> 52);      // 12 bits
+      while (true) {
+        const uint64_t cur = hk[h];
+        if (cur == km) break;
+        if (cur == ~0ull) {
+          const unsigned long long old = atomicCAS((unsigned long long *)&hk[h], ~0ull, (unsigned long long)km);
+          if (old == ~0ull) { if (atomicAdd(&n_dist, 1u) >= BK_MAXDIST) bad = 1; break; }
+          if (old == km) break;
+        }
+        if (bad) break;
+        h = (h + 1) & (BK_TABLE - 1);
+      }
+      ts[i] = (uint16_t)((h << 3) | cls);
+      atomicAdd(&hc[h * 5 + cls], 1u);
+    }
+    __syncthreads();
+    if (bad) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
+    //  exclusive prefix sum over hc[slot * 5 + class] in slot order: every thread owns 40 consecutive entries
+    {
+      const int per = BK_TABLE * 5 / BK_THREADS;
+      uint32_t sum = 0;
+      for (int j = 0; j < per; j++) sum += hc[tid * per + j];
+      uint32_t inc = sum;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        uint32_t w = lane < BK_THREADS / 32 ? wsum[lane] : 0, wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+        if (lane < BK_THREADS / 32) wsum[lane] = wi - w;
+      }
+      __syncthreads();
+      uint32_t run = wsum[wid] + inc - sum;
+      for (int j = 0; j < per; j++) { const uint32_t c = hc[tid * per + j]; hc[tid * per + j] = run; run += c; }
+    }
+    if (tid == 0) {
+      const unsigned int nd = n_dist;
+      const unsigned long long base = atomicAdd(&out[0], (unsigned long long)nd);
+      slot_base = (base + nd <= tmp_cap) ? (unsigned int)base : 0xFFFFFFFFu;
+      if (base + nd > tmp_cap) atomicOr(&out[1], 1ull);
+    }
+    __syncthreads();
+    //  scatter the positions to their segment: hc becomes the END of every (slot, class)
+    for (uint32_t i = tid; i < m; i += BK_THREADS) {
+      const uint32_t sc = ts[i];
+      const uint32_t dst = atomicAdd(&hc[(sc >> 3) * 5 + (sc & 7u)], 1u);
+      gpos[dst] = tp[i];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += BK_THREADS) occ[s0 + i] = gpos[i];
+    //  one slot record per occupied table entry
+    if (slot_base != 0xFFFFFFFFu) {
+      for (int base_h = 0; base_h < BK_TABLE; base_h += BK_THREADS) {
+        const int h = base_h + tid;
+        const bool occd = hk[h] != ~0ull;
+        const unsigned bm = __ballot_sync(0xffffffffu, occd);
+        if (lane == 0) wsum[wid] = __popc(bm);
+        __syncthreads();
+        uint32_t before = 0;
+        for (int w = 0; w < wid; w++) before += wsum[w];
+        uint32_t total = 0;
+        for (int w = 0; w < BK_THREADS / 32; w++) total += wsum[w];
+        if (occd) {
+          const uint32_t c = slot_base + before + __popc(bm & ((1u << lane) - 1));
+          const uint32_t st = h ? hc[h * 5 - 1] : 0u;
+          const uint32_t e0 = hc[h * 5], e1 = hc[h * 5 + 1], e2 = hc[h * 5 + 2], e3 = hc[h * 5 + 3], e4 = hc[h * 5 + 4];
+          uint32_t mp = 0xFFFFFFFFu;
+          for (uint32_t j = st; j < e4; j++) { const uint32_t p = gpos[j]; if (p < mp) mp = p; }
+          const uint64_t kmer = (hk[h] * mix_inv) & kmask;
+          uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
+          sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), s0 + st, s0 + e0);
+          sp[1] = make_uint4(s0 + e1, s0 + e2, s0 + e3, s0 + e4);
+          gk[c] = mp; gv[c] = c;
+        }
+        __syncthreads();
+        if (tid == 0) slot_base += total;
+        __syncthreads();
+      }
+    }
+  }
 }
 
 //  counts distinct k-mers and finds the number of valid tuples in the sorted array
@@ -889,39 +1077,105 @@ int ovl_build_index(ovlb_ctx *c) {
   if ((rc = ensure(X.tval, X.tval_cap, (size_t)n + 32))) return rc;
   if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
 
-  //  (k-mer, class of the preceding base) -> position, one tuple per window
-  EvTimer t1(c->stream);
-  if (n_groups) {
-    k_hash_tuples<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.tkey, X.tval);
-    c->launches++;
-  }
-  CK(cudaGetLastError());
-  c->timings.index_tuples_ms = t1.stop();
+  //  Bucketed build (default) or sorted build (OVLB_BUCKETED=0, or after a bucket overflowed)
+  static int bucketed_env = -1;
+  if (bucketed_env < 0) { const char *ev = getenv("OVLB_BUCKETED"); bucketed_env = ev ? atoi(ev) : 1; }
+  bool bucketed = bucketed_env != 0;
+  const uint64_t mixc = 0x9E3779B97F4A7C15ull;
+  uint64_t mix_inv = mixc;                                              // inverse mod 2^64 by Newton iteration
+  for (int i = 0; i < 6; i++) mix_inv *= 2 - mixc * mix_inv;
+  bool tmp_ready = false;
 
-  EvTimer t2(c->stream);
-  if (n) {
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream);
-    if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
-    size_t tb2 = c->cub_temp_cap;
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream));
-    c->launches += 2 + (2 * K + 4 + 7) / 8;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    //  (k-mer, class of the preceding base) -> position, one tuple per window
+    EvTimer t1(c->stream);
+    uint64_t nt = n;                                                      // tuples to partition / sort
+    if (n_groups && bucketed) {
+      CK(cudaMemsetAsync(&c->d_work[5], 0, 8, c->stream));
+      k_hash_tuples_compact<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K,
+                                                                                           mixc, X.tkey, X.tval, &c->d_work[5]);
+      unsigned long long nv = 0;
+      CK(cudaMemcpyAsync(&nv, &c->d_work[5], 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      nt = nv;
+      c->launches++;
+    } else if (n_groups) {
+      k_hash_tuples<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.tkey, X.tval);
+      c->launches++;
+    }
+    CK(cudaGetLastError());
+    c->timings.index_tuples_ms = t1.stop();
+    if (bucketed && nt < (1u << 16)) { bucketed = false; continue; }      // tiny block: the sorted build
+
+    if (bucketed) {
+      //  number of buckets: a power of two with ~BK_TARGET tuples each, cut out of the top bits of the 2K+3-bit key
+      int B = 8; while (B < 2 * K && (nt >> B) > BK_TARGET) B++;
+      const uint32_t nb = 1u << B;
+      const int shift = 2 * K + 3 - B;
+      const uint64_t tmp_cap = nt / 4 * 3 + (1u << 20);
+      EvTimer t2(c->stream);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)nt, shift, 2 * K + 3, c->stream);
+      const size_t offs_at = (tb + 255) & ~(size_t)255;
+      if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, offs_at + ((size_t)nb + 1) * 4 + 256))) return rc;
+      uint32_t *offs = reinterpret_cast<uint32_t *>((uint8_t *)c->cub_temp + offs_at);
+      size_t tb2 = tb;
+      //  tkey/tval -> tkey2/occ (partitioned); the grouped positions then go back into tval, which becomes `occ`
+      CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)nt, shift, 2 * K + 3, c->stream));
+      k_bucket_offsets<<<div_up(nb + 1, 256), 256, 0, c->stream>>>(X.tkey2, nt, shift, nb, offs);
+      c->launches += 2 + (B + 7) / 8;
+      CK(cudaGetLastError());
+      c->timings.index_sort_ms = t2.stop();
+
+      EvTimer t3(c->stream);
+      if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
+      if ((rc = ensure(X.gk, X.gk_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
+      if ((rc = ensure(X.gv, X.gv_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
+      CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
+      static bool attr_set = false;
+      if (!attr_set) { CK(cudaFuncSetAttribute(k_bucket_group, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM)); attr_set = true; }
+      k_bucket_group<<<c->sm_count, BK_THREADS, BK_SMEM, c->stream>>>(X.tkey2, X.occ, offs, nb, K, mix_inv, X.tval, X.tmp_slots,
+                                                                        (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, X.gv, &c->d_work[5]);
+      c->launches++;
+      unsigned long long h3[2] = {0, 0};
+      CK(cudaMemcpyAsync(h3, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaGetLastError());
+      c->timings.index_table_ms = t3.stop();
+      if (h3[1] != 0) { bucketed = false; continue; }                     // a bucket did not fit: redo with the sorted build
+      X.n_distinct = h3[0];
+      X.n_occ = nt;
+      std::swap(X.tval, X.occ); std::swap(X.tval_cap, X.occ_cap);        // grouped positions are the occurrence lists
+      tmp_ready = true;
+      break;
+    }
+
+    EvTimer t2(c->stream);
+    if (n) {
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream);
+      if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, tb + 256))) return rc;
+      size_t tb2 = c->cub_temp_cap;
+      CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)n, 0, 2 * K + 4, c->stream));
+      c->launches += 2 + (2 * K + 4 + 7) / 8;
+    }
+    CK(cudaGetLastError());
+    c->timings.index_sort_ms = t2.stop();
+
+    unsigned long long h2[2] = {0, 0};
+    CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
+    if (n) {
+      k_count_distinct<<<div_up(n, 256 * CNT_PER_THREAD), 256, 0, c->stream>>>(X.tkey2, n, sentinel, &c->d_work[5]);
+      c->launches++;
+    }
+    CK(cudaMemcpyAsync(h2, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    X.n_distinct = h2[0];
+    X.n_occ = h2[1];
+    break;
   }
-  CK(cudaGetLastError());
-  c->timings.index_sort_ms = t2.stop();
 
   EvTimer t3(c->stream);
-  unsigned long long h2[2] = {0, 0};
-  CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
-  if (n) {
-    k_count_distinct<<<div_up(n, 256 * CNT_PER_THREAD), 256, 0, c->stream>>>(X.tkey2, n, sentinel, &c->d_work[5]);
-    c->launches++;
-  }
-  CK(cudaMemcpyAsync(h2, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  X.n_distinct = h2[0];
-  X.n_occ = h2[1];
-
   //  slots in discovery order + the key of the path order (first position), then the path sort and the gather
   std::vector<uint64_t> skip(c->skip_keys);
   std::sort(skip.begin(), skip.end());
@@ -930,18 +1184,22 @@ int ovl_build_index(ovlb_ctx *c) {
   if (ns >= 0xFFFFFFF0ull) { ovl_set_error("too many distinct k-mers for one index (>= 2^32); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
   uint64_t hcap = ((2 * ns + 64) + 7) & ~7ull;            // whole 128-byte lines of eight entries, load <= 0.5
   if ((rc = ensure(X.slots, X.slots_cap, (size_t)ns + 1, 9, 8))) return rc;
-  if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if (!tmp_ready) {
+    if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)nd + 1, 9, 8))) return rc;
+    if ((rc = ensure(X.gk, X.gk_cap, (size_t)nd + 1, 9, 8))) return rc;
+    if ((rc = ensure(X.gv, X.gv_cap, (size_t)nd + 1, 9, 8))) return rc;
+  }
   if ((rc = ensure(X.htab, X.htab_cap, (size_t)hcap, 9, 8))) return rc;
-  if ((rc = ensure(X.gk, X.gk_cap, (size_t)nd + 1, 9, 8))) return rc;
-  if ((rc = ensure(X.gv, X.gv_cap, (size_t)nd + 1, 9, 8))) return rc;
   if ((rc = ensure(X.gk2, X.gk2_cap, (size_t)nd + 1, 9, 8))) return rc;
   if ((rc = ensure(X.gv2, X.gv2_cap, (size_t)nd + 1, 9, 8))) return rc;
   X.hcap = hcap; X.n_slots = (uint32_t)nd;
   CK(cudaMemsetAsync(X.htab, 0xFF, hcap * sizeof(HashEntry), c->stream));
   CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
   if (X.n_occ) {
-    k_group_heads<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, X.occ, (uint32_t)X.n_occ, X.tmp_slots, X.gk, X.gv, &c->d_work[5]);
-    c->launches++;
+    if (!tmp_ready) {
+      k_group_heads<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, X.occ, (uint32_t)X.n_occ, X.tmp_slots, X.gk, X.gv, &c->d_work[5]);
+      c->launches++;
+    }
     int end_bit = 1; while (end_bit < 32 && (H.n_pos >> end_bit)) end_bit++;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, X.gk, X.gk2, X.gv, X.gv2, (int64_t)nd, 0, end_bit, c->stream);
@@ -953,7 +1211,7 @@ int ovl_build_index(ovlb_ctx *c) {
     c->launches++;
   }
   CK(cudaGetLastError());
-  c->timings.index_table_ms = t3.stop();
+  c->timings.index_table_ms = (tmp_ready ? c->timings.index_table_ms : 0.0f) + t3.stop();
   c->host_counters[CT_HASH_KMERS] += X.n_occ;
 
   EvTimer t4(c->stream);
