@@ -332,11 +332,14 @@ def main():
         # brackets on the library's stream around each kernel (group) of the step; a stage of n identical launches
         # (the radix-sort passes) is divided by n: `achieved` is algorithmic bytes PER LAUNCH over time PER LAUNCH.
         hk, rk, sh, sr = (ctr[x] / args.steps for x in ("hash_kmers", "ref_kmers", "seed_hits", "seed_runs"))
-        sort_passes = (2 * K + 4 + 7) // 8
+        bbits = 8                                                   # bucket bits of the bucketed index build (ovl_build_index)
+        while bbits < 2 * K and (int(hk) >> bbits) > 4096:
+            bbits += 1
+        sort_passes = (bbits + 7) // 8
         stage_def = {   # stage: (kernel, launches, algorithmic bytes per launch)
-            "index_tuples_ms": ("k_hash_tuples", 1, hk * (0.5 + 12)),             # dp4 base read + (key, position) tuple write
-            "index_sort_ms": ("cub::DeviceRadixSortOnesweep (one 8-bit pass)", sort_passes, hk * 12 * 2),   # every pass reads and writes every 12 B tuple
-            "index_table_ms": ("k_group_heads + path sort + k_path_slots", 1, hk * 12 + 0),       # sorted tuples read once (+ 3 x 32 B per distinct k-mer, not counted)
+            "index_tuples_ms": ("k_hash_tuples_compact", 1, hk * (0.5 + 12)),             # dp4 base read + (key, position) tuple write
+            "index_sort_ms": ("cub::DeviceRadixSortOnesweep (one 8-bit pass over the bucket bits)", sort_passes, hk * 12 * 2),   # every pass reads and writes every 12 B tuple
+            "index_table_ms": ("k_bucket_group + path sort + k_path_slots", 1, hk * (12 + 4)),    # partitioned tuples read once, grouped positions written (+ 3 x 32 B per distinct k-mer, not counted)
             "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),                      # dp4 base + one 32 B slot per window
             "expand_ms": ("k_expand_small + k_expand_large", 1, sr * (4 + 16 + 16)),   # occurrence + bases compared + run record written
             "sort_ms": ("cub::DeviceRadixSortOnesweep (runs)", 8, sr * 16 * 2),

@@ -76,7 +76,7 @@ EXPORTS = [
     "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
-    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend",
+    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
     "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_assign_tiles",
 ]
@@ -114,6 +114,7 @@ def load_library():
     L.ovlb_debug_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
+    L.ovlb_debug_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ovlb_params_init.argtypes = [C.POINTER(_Params), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.ovlb_params_free.argtypes = [C.POINTER(_Params)]
@@ -319,6 +320,11 @@ class Overlapper:
         return ms.value
 
     # --- debug taps (tests) ---
+    def debug_index_info(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(self.L.ovlb_debug_index_info(self._h, out))
+        return {"distinct": out[0], "occurrences": out[1], "slots": out[2], "bucketed": bool(out[3])}
+
     def debug_pairs(self):
         np_, ns_ = C.c_uint64(), C.c_uint64()
         self.L.ovlb_debug_pairs(self._h, None, 0, C.byref(np_), None, 0, C.byref(ns_))

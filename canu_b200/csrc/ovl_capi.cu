@@ -273,6 +273,13 @@ int ovlb_timer_stop(ovlb_ctx *c, float *ms) {
   return OVLB_OK;
 }
 
+int ovlb_debug_index_info(ovlb_ctx *c, uint64_t out[4]) {
+  if (!c || !out) { ovl_set_error("ovlb_debug_index_info: null argument"); return OVLB_ERR_ARG; }
+  if (!c->index.built) { ovl_set_error("ovlb_debug_index_info: no index built"); return OVLB_ERR_STATE; }
+  out[0] = c->index.n_distinct; out[1] = c->index.n_occ; out[2] = c->index.n_slots; out[3] = c->index.bucketed ? 1 : 0;
+  return OVLB_OK;
+}
+
 int ovlb_debug_pairs(ovlb_ctx *c, ovlb_pair_info *pairs, uint64_t pair_cap, uint64_t *n_pairs,
                      ovlb_seed *seeds, uint64_t seed_cap, uint64_t *n_seeds) {
   if (!c || !n_pairs || !n_seeds) { ovl_set_error("ovlb_debug_pairs: null argument"); return OVLB_ERR_ARG; }

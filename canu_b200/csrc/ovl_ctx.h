@@ -48,6 +48,7 @@ struct DevIndex {
   uint32_t  *occ = nullptr;       // [n_occ] hash position index of each occurrence, sorted by (k-mer, class)
   uint64_t   n_occ = 0, n_distinct = 0;
   bool       built = false;
+  bool       bucketed = false;    // the bucketed build produced this index (else: the sorted build)
   uint64_t  *tkey = nullptr, *tkey2 = nullptr;   // build scratch: (k-mer << 3 | class) before / after the sort
   uint32_t  *tval = nullptr;                     // build scratch: position index before the sort
   IndexSlot *tmp_slots = nullptr;                // build scratch: slots in discovery order

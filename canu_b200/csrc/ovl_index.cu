@@ -1146,9 +1146,11 @@ int ovl_build_index(ovlb_ctx *c) {
       X.n_distinct = h3[0];
       X.n_occ = nt;
       std::swap(X.tval, X.occ); std::swap(X.tval_cap, X.occ_cap);        // grouped positions are the occurrence lists
+      X.bucketed = true;
       tmp_ready = true;
       break;
     }
+    X.bucketed = false;
 
     EvTimer t2(c->stream);
     if (n) {

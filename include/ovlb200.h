@@ -193,6 +193,11 @@ typedef struct { int32_t start, offset, len; } ovlb_seed;
 int  ovlb_debug_pairs(ovlb_ctx *ctx, ovlb_pair_info *pairs, uint64_t pair_cap, uint64_t *n_pairs,
                       ovlb_seed *seeds, uint64_t seed_cap, uint64_t *n_seeds);
 
+/*  Shape of the index built last: out[0] distinct k-mers, out[1] occurrences, out[2] slots (distinct + skip k-mers no
+ *  hash read holds), out[3] 1 if the bucketed build produced it, 0 if the sorted build did (tiny block, a bucket that
+ *  did not fit shared memory, or OVLB_BUCKETED=0).  */
+int  ovlb_debug_index_info(ovlb_ctx *ctx, uint64_t out[4]);
+
 /*  Extend one seed between two reads already on the device (ref batch read
  *  `ref_index` in orientation `dir`, hash read `hash_index`) exactly as
  *  Extend_Alignment would; out[0..7) = s_lo, s_hi, t_lo, t_hi, errors, kind, delta_ct.

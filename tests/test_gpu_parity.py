@@ -196,10 +196,13 @@ def test_empty_and_degenerate_inputs():
     assert len(recs) == 1 and (recs[0]["a_iid"], recs[0]["b_iid"]) == (3, 1)
 
 
-@pytest.mark.parametrize("case", ["A_default", "A_skip", "A_partial", "A_ranges", "C_hpc"])
-def test_drop_in_executable_on_sqstore(case, tmp_path):
+@pytest.mark.parametrize("case,build_env", [("A_default", {}), ("A_skip", {}), ("A_partial", {}), ("A_ranges", {}), ("C_hpc", {}),
+                                            ("A_default", {"OVLB_BUCKETED": "0"}), ("A_skip", {"OVLB_BUCKETED": "0"}),
+                                            ("B_e06", {"OVLB_BUCKETED": "0"})])
+def test_drop_in_executable_on_sqstore(case, build_env, tmp_path):
     """The C++ host driver end to end: same argv as the reference, reads the reference-made sqStore,
-    writes .ovb/.oc/.stats; compared with the golden output of the reference binary."""
+    writes .ovb/.oc/.stats; compared with the golden output of the reference binary.  OVLB_BUCKETED=0 forces the
+    sorted index build (the fallback of the bucketed one) so that both builds stay pinned to the goldens."""
     import os
     import subprocess
     _api()
@@ -213,7 +216,7 @@ def test_drop_in_executable_on_sqstore(case, tmp_path):
     ovb = str(tmp_path / "out.ovb")
     cmd = [exe, "-t", "4", "-k", "22", "--hashbits", "22", "--hashload", "0.8", "--minlength", "500"] + flags + [
         "-h", "%d-%d" % tuple(c["h"]), "-r", "%d-%d" % tuple(c["r"]), "-o", ovb, "-s", str(tmp_path / "out.stats"), store]
-    r = subprocess.run(cmd, capture_output=True)
+    r = subprocess.run(cmd, capture_output=True, env=dict(os.environ, **build_env))
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     lines = subprocess.check_output([tool, "dump-ovb", ovb]).decode().splitlines()
     recs = np.zeros(len(lines), dtype=[("a_iid", "<u4"), ("b_iid", "<u4"), ("w0", "<u8"), ("w1", "<u8")])
@@ -255,3 +258,49 @@ def test_drop_in_executable_multi_worker(extra, tmp_path):
     assert got == want, _diff_msg(got, want)
     assert open(str(tmp_path / "out.stats")).read() == open(os.path.join(gu.GOLDEN, "A_default.stats")).read()
     assert open(str(tmp_path / "out.oc"), "rb").read() == open(os.path.join(gu.GOLDEN, "A_default.oc"), "rb").read()
+
+
+def test_index_build_paths_agree_and_overflow_falls_back():
+    """The bucketed index build is the default; a k-mer with more occurrences than a bucket holds (a 300-copy repeat
+    at 30x) makes it fall back to the sorted build.  Both must give the oracle's overlaps; the repeat's k-mers are on
+    the skip list (as Canu's meryl step would put them), which keeps the candidate pairs to the unique sequence but
+    still sends every occurrence through the index build."""
+    from oracle import oracle_py as op
+    from canu_b200 import synth
+    api = _api()
+    K = 22
+
+    def run(genome, skip_unit):
+        reads = synth.simulate_reads(genome, 30, 1500, 4000, 0.01, seed=78)
+        prm = api.OverlapParams(kmer_len=K, max_erate=0.045, min_olap_len=500, max_read_len=max(r.size for r in reads))
+        skip = None
+        if skip_unit is not None:
+            skip = [skip_unit[i:i + K].tobytes().decode() for i in range(len(skip_unit) - K + 1)]   # both sides add the reverse complements
+        ov = api.Overlapper(prm)
+        pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+        ov.load_hash_reads(pk)
+        if skip:
+            ov.mark_skip_kmers(skip)
+        ov.build_index()
+        info = ov.debug_index_info()
+        recs = ov.overlap_ref_batch(pk, cap=1 << 22)
+        ov.close()
+        o = op.Oracle(kmer_len=K, max_erate=0.045, min_olap_len=500, hash_bits=18, hash_load=0.8)
+        o.set_reads(reads)
+        if skip:
+            o.set_skip_kmers(skip)
+        want = op.sort_records(o.run(threads=8))
+        got = np.sort(recs, order=["a_iid", "b_iid", "w0", "w1"])
+        assert len(got) == len(want) and len(got) > 0
+        for f in ("a_iid", "b_iid", "w0", "w1"):
+            assert np.array_equal(got[f], want[f]), f
+        return info
+
+    plain = synth.make_genome(120000, seed=77)
+    info = run(plain, None)
+    assert info["bucketed"], info                      # 3.6 M tuples: the bucketed build handles it
+    rep = synth.make_genome(300000, seed=79, repeat_len=300, repeat_copies=300)
+    step = 300000 // 300
+    unit = rep[step // 3: step // 3 + 300]
+    info = run(rep, unit)
+    assert not info["bucketed"], info                  # ~9000 occurrences of every repeat k-mer: a bucket overflowed
