@@ -209,7 +209,7 @@ k_hash_tuples_compact(const uint64_t *__restrict__ fwd, const uint64_t *__restri
 #define BK_TARGET  4096                 // mean bucket size the bucket count is chosen for
 #define BK_TABLE   4096                 // hash-table entries per bucket
 #define BK_MAXDIST 3584                 // distinct k-mers a bucket may hold (load 0.875)
-#define BK_SMEM    (BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 8 + BK_TABLE * 5 * 4 + 64)
+#define BK_SMEM    (BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 8 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
 
 //  first tuple of every bucket (bucket = key >> shift) in the partitioned tuple array; offs[nb] = n
 __global__ void k_bucket_offsets(const uint64_t *__restrict__ key, uint64_t n, int shift, uint32_t nb, uint32_t *__restrict__ offs) {
@@ -233,6 +233,7 @@ k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ p
   uint16_t *ts = reinterpret_cast<uint16_t *>(tp + BK_CAP);              // [BK_CAP] slot << 3 | class
   uint64_t *hk = reinterpret_cast<uint64_t *>(ts + BK_CAP);              // [BK_TABLE] mixed k-mer of the slot
   uint32_t *hc = reinterpret_cast<uint32_t *>(hk + BK_TABLE);            // [BK_TABLE * 5] count -> start -> end of (slot, class)
+  uint32_t *hm = hc + BK_TABLE * 5;                                      // [BK_TABLE] first (smallest) position of the slot's k-mer
   __shared__ unsigned int n_dist, bad, slot_base;
   __shared__ unsigned int wsum[BK_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -244,7 +245,7 @@ k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ p
     if (m == 0) continue;
     if (m > BK_CAP) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
     __syncthreads();                                                     // previous bucket fully written out
-    for (int i = tid; i < BK_TABLE; i += BK_THREADS) hk[i] = ~0ull;
+    for (int i = tid; i < BK_TABLE; i += BK_THREADS) { hk[i] = ~0ull; hm[i] = 0xFFFFFFFFu; }
     for (int i = tid; i < BK_TABLE * 5; i += BK_THREADS) hc[i] = 0;
     if (tid == 0) { n_dist = 0; bad = 0; }
     __syncthreads();
@@ -278,6 +279,7 @@ k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ p
       }
       ts[i] = (uint16_t)((h << 3) | cls);
       atomicAdd(&hc[h * 5 + cls], 1u);
+      atomicMin(&hm[h], preg[j]);
     }
     __syncthreads();
     if (bad) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
@@ -316,33 +318,37 @@ k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ p
     }
     __syncthreads();
     for (uint32_t i = tid; i < m; i += BK_THREADS) occ[s0 + i] = gpos[i];
-    //  one slot record per occupied table entry
+    //  one slot record per occupied table entry: every thread owns BK_TABLE / BK_THREADS consecutive entries
     if (slot_base != 0xFFFFFFFFu) {
-      for (int base_h = 0; base_h < BK_TABLE; base_h += BK_THREADS) {
-        const int h = base_h + tid;
-        const bool occd = hk[h] != ~0ull;
-        const unsigned bm = __ballot_sync(0xffffffffu, occd);
-        if (lane == 0) wsum[wid] = __popc(bm);
-        __syncthreads();
-        uint32_t before = 0;
-        for (int w = 0; w < wid; w++) before += wsum[w];
-        uint32_t total = 0;
-        for (int w = 0; w < BK_THREADS / 32; w++) total += wsum[w];
-        if (occd) {
-          const uint32_t c = slot_base + before + __popc(bm & ((1u << lane) - 1));
-          const uint32_t st = h ? hc[h * 5 - 1] : 0u;
-          const uint32_t e0 = hc[h * 5], e1 = hc[h * 5 + 1], e2 = hc[h * 5 + 2], e3 = hc[h * 5 + 3], e4 = hc[h * 5 + 4];
-          uint32_t mp = 0xFFFFFFFFu;
-          for (uint32_t j = st; j < e4; j++) { const uint32_t p = gpos[j]; if (p < mp) mp = p; }
-          const uint64_t kmer = (hk[h] * mix_inv) & kmask;
-          uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
-          sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), s0 + st, s0 + e0);
-          sp[1] = make_uint4(s0 + e1, s0 + e2, s0 + e3, s0 + e4);
-          gk[c] = mp; gv[c] = c;
-        }
-        __syncthreads();
-        if (tid == 0) slot_base += total;
-        __syncthreads();
+      const int per = BK_TABLE / BK_THREADS;
+      uint32_t mine = 0;
+      #pragma unroll
+      for (int j = 0; j < per; j++) mine += hk[tid * per + j] != ~0ull;
+      uint32_t inc = mine;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        uint32_t w = wsum[lane], wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+        wsum[lane] = wi - w;
+      }
+      __syncthreads();
+      uint32_t c = slot_base + wsum[wid] + inc - mine;
+      #pragma unroll
+      for (int j = 0; j < per; j++) {
+        const int h = tid * per + j;
+        const uint64_t km = hk[h];
+        if (km == ~0ull) continue;
+        const uint32_t st = h ? hc[h * 5 - 1] : 0u;
+        const uint64_t kmer = (km * mix_inv) & kmask;
+        uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
+        sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), s0 + st, s0 + hc[h * 5]);
+        sp[1] = make_uint4(s0 + hc[h * 5 + 1], s0 + hc[h * 5 + 2], s0 + hc[h * 5 + 3], s0 + hc[h * 5 + 4]);
+        gk[c] = hm[h]; gv[c] = c;
+        c++;
       }
     }
   }
