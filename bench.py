@@ -16,7 +16,8 @@ candidate pair, overlap records packed on the device.
          "Kmer hits with olaps + Kmer hits without olaps" of the -s file), device pipeline only,
          reads already resident in HBM (dp4-encoded) when the timed region starts.
   e2e    the same metric through the C ABI with HOST buffers: packed reads copied host->device for
-         the hash and ref side, records copied device->host, inside the timed region.
+         the hash and ref side, records copied device->host, inside the timed region (the ref batch's
+         upload is issued before ovlb_build_index and runs on the library's copy stream beside it).
   roofline  the longest HBM-bound kernel launch of the step (by measured time per launch) against the measured
          HBM peak; `stage_rooflines` lists every HBM-bound stage the same way.  The extension kernel is integer-ALU
          bound (no GEMM shape, no tensor cores) and is reported under `extension` (HiFi tile of the step) and
@@ -256,9 +257,11 @@ def main():
     api._check(api.load_library().ovlb_host_register(rec_host.ctypes.data, rec_host.nbytes))
 
     def e2e_step():
-        ov.load_hash_reads(packed)
+        ov.load_hash_reads(packed)                 # H2D of the hash block + encode (compute stream)
+        ov.stage_ref_batch(packed)                 # H2D of the ref batch + encode on the copy stream: overlaps the index build
         ov.build_index()
-        k = ov.overlap_ref_batch_into(packed, rec_host)
+        ov.run_staged()                            # waits for the ref upload, then seeding + extension
+        k = ov.fetch_records_into(rec_host)        # D2H of the records
         return rec_host[:k]
 
     e2e_step()

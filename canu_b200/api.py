@@ -276,7 +276,14 @@ class Overlapper:
         return out[: n.value].copy()
 
     def stage_ref_batch(self, packed: PackedReads):
+        """Upload + encode a ref batch on the copy stream; may precede build_index() (the upload then overlaps it)."""
+        self._staged_src = packed                      # the buffers must outlive the asynchronous upload
         _check(self.L.ovlb_stage_ref_batch(self._h, C.cast(packed.view, C.c_void_p)))
+
+    def fetch_records_into(self, out: np.ndarray) -> int:
+        n = C.c_uint64()
+        _check(self.L.ovlb_fetch_records(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return n.value
 
     def run_staged(self) -> int:
         n = C.c_uint64()

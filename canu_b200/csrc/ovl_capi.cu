@@ -72,6 +72,9 @@ int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   //  the index is probed one 32-byte sector at a time at random: do not let L2 fetch 64/128 B around each miss
   cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32); cudaGetLastError();
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming));
+  CK(cudaEventCreate(&c->ref_up0)); CK(cudaEventCreate(&c->ref_up1));
   CK(cudaMalloc((void **)&c->d_eml, (size_t)p->n_edit_match_limit * 4));
   CK(cudaMemcpyAsync(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice, c->stream));
   c->P.edit_match_limit = nullptr;                     // caller's buffer is not retained
@@ -104,16 +107,20 @@ void ovlb_destroy(ovlb_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   free_reads(c->hash); free_reads(c->ref);
   void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.slots, c->index.htab, c->index.tmp_slots, c->index.gk, c->index.gv, c->index.gk2, c->index.gv2,
                    c->index.occ, c->index.tkey, c->index.tkey2, c->index.tval,
                    c->ext.arena, c->ext.row_left, c->ext.row_off, c->ext.gring, c->ext.path, c->ext.ival, c->ext.ikc, c->ext.ldelta, c->ext.rdelta,
-                   c->d_packed, c->d_boff, c->d_nread, c->d_npos, c->ref_valid, c->item_small, c->item_large,
+                   c->stg[0].d_packed, c->stg[0].d_boff, c->stg[0].d_nread, c->stg[0].d_npos,
+                   c->stg[1].d_packed, c->stg[1].d_boff, c->stg[1].d_nread, c->stg[1].d_npos, c->ref_valid, c->item_small, c->item_large,
                    c->run_key, c->run_val, c->run_key2, c->run_val2, c->runs_extra, c->pair_flag, c->pair_idx, c->cub_temp, c->pairs,
                    c->seed_start, c->seed_off, c->seed_len, c->sim_nxt, c->sim_hits, c->sim_act, c->sim_order, c->seed_alive, c->d_records };
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->ev_start) { cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); }
   cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ref_ready) { cudaEventDestroy(c->ref_ready); cudaEventDestroy(c->ref_up0); cudaEventDestroy(c->ref_up1); }
   delete c;
 }
 
@@ -146,7 +153,6 @@ int ovlb_build_index(ovlb_ctx *c) {
 int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
   if (!c || !reads) { ovl_set_error("ovlb_stage_ref_batch: null argument"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
-  if (!c->index.built) { ovl_set_error("ovlb_stage_ref_batch: build the index first"); return OVLB_ERR_STATE; }
   c->staged = false;
   int rc = ovl_upload_reads(c, reads, c->ref, false, &c->timings.upload_ms, &c->timings.encode_ms);
   if (rc) return rc;
@@ -158,6 +164,14 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
   if (!c) { ovl_set_error("ovlb_run_staged: null context"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   if (!c->staged) { ovl_set_error("ovlb_run_staged: no staged ref batch"); return OVLB_ERR_STATE; }
+  if (!c->index.built) { ovl_set_error("ovlb_run_staged: build the index first"); return OVLB_ERR_STATE; }
+  if (c->ref_pending) {                                  // the upload ran beside whatever the caller did since staging
+    CK(cudaStreamWaitEvent(c->stream, c->ref_ready, 0));
+    CK(cudaEventSynchronize(c->ref_up1));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ref_up0, c->ref_up1);
+    c->timings.upload_ms = ms; c->timings.encode_ms = 0;
+    c->ref_pending = false;
+  }
   EvT tt(c->stream);
   c->n_records = 0;
   int rc = ovl_seed_ref_batch(c);

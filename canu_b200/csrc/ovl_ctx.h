@@ -115,9 +115,16 @@ struct ovlb_ctx {
   int          sm_count = 148;
 
   //  staging
-  uint8_t  *d_packed = nullptr;   size_t packed_cap = 0;
-  uint64_t *d_boff = nullptr;     size_t boff_cap = 0;
-  uint32_t *d_nread = nullptr, *d_npos = nullptr; size_t nn_cap = 0;
+  //  one set per side (0 = hash, 1 = ref): the ref batch is uploaded on `copy_stream` while the index is being built
+  struct Staging {
+    uint8_t  *d_packed = nullptr;   size_t packed_cap = 0;
+    uint64_t *d_boff = nullptr;     size_t boff_cap = 0;
+    uint32_t *d_nread = nullptr, *d_npos = nullptr; size_t nn_cap = 0;
+    std::vector<uint64_t> h_woff, h_pbase;          // host copies that must outlive the asynchronous upload
+  } stg[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t  ref_ready = nullptr, ref_up0 = nullptr, ref_up1 = nullptr;   // ref upload + encode done; brackets for its timing
+  bool         ref_pending = false;                   // a ref upload is in flight on copy_stream
   uint8_t  *h_pinned = nullptr;   size_t pinned_cap = 0;
   std::vector<uint64_t> skip_keys;
 

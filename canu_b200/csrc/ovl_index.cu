@@ -1006,6 +1006,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   if (maxlen > c->P.max_read_len) { ovl_set_error("read longer than ovlb_params.max_read_len"); return OVLB_ERR_ARG; }
 
   int rc;
+  if (!is_hash && c->ref_pending) { CK(cudaStreamSynchronize(c->copy_stream)); c->ref_pending = false; }   // previous upload still in flight
   if (nw + 4 > dst.cap_words) {
     if (dst.fwd) cudaFree(dst.fwd); if (dst.rc) cudaFree(dst.rc);
     dst.fwd = dst.rc = nullptr; dst.cap_words = 0;
@@ -1025,38 +1026,54 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   }
   dst.n = n; dst.first_id = in->first_read_id; dst.total_bases = tb; dst.n_words = nw; dst.n_pos = np; dst.n_windows = nwin; dst.max_len = maxlen;
 
-  EvTimer tu(c->stream);
-  if ((rc = ensure(c->d_packed, c->packed_cap, (size_t)in->packed_bytes + 16))) return rc;
-  if ((rc = ensure(c->d_boff, c->boff_cap, (size_t)n + 1))) return rc;
-  if (in->packed_bytes) CK(cudaMemcpyAsync(c->d_packed, in->packed, in->packed_bytes, cudaMemcpyHostToDevice, c->stream));
-  if (n) {
-    CK(cudaMemcpyAsync(c->d_boff, in->byte_offset, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(dst.len, in->len, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  //  Hash side: on the compute stream, synchronous (the index build follows).  Ref side: on the copy stream, asynchronous
+  //  when the caller's buffers are page-locked -- it overlaps the index build or the previous batch's host work;
+  //  ovlb_run_staged makes the compute stream wait for `ref_ready`.
+  ovlb_ctx::Staging &S = c->stg[is_hash ? 0 : 1];
+  cudaStream_t st = is_hash ? c->stream : c->copy_stream;
+  S.h_woff.swap(woff); S.h_pbase.swap(pbase);
+  if ((rc = ensure(S.d_packed, S.packed_cap, (size_t)in->packed_bytes + 16))) return rc;
+  if ((rc = ensure(S.d_boff, S.boff_cap, (size_t)n + 1))) return rc;
+  if (in->n_n > S.nn_cap) {
+    if (S.d_nread) cudaFree(S.d_nread); if (S.d_npos) cudaFree(S.d_npos);
+    S.nn_cap = in->n_n * 5 / 4 + 64;
+    CK(cudaMalloc((void **)&S.d_nread, S.nn_cap * 4));
+    CK(cudaMalloc((void **)&S.d_npos, S.nn_cap * 4));
   }
-  CK(cudaMemcpyAsync(dst.woff, woff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(dst.pbase, pbase.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (is_hash) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); CK(cudaEventRecord(e0, st)); }
+  else CK(cudaEventRecord(c->ref_up0, st));
+  if (in->packed_bytes) CK(cudaMemcpyAsync(S.d_packed, in->packed, in->packed_bytes, cudaMemcpyHostToDevice, st));
+  if (n) {
+    CK(cudaMemcpyAsync(S.d_boff, in->byte_offset, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dst.len, in->len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(dst.woff, S.h_woff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dst.pbase, S.h_pbase.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
   if (in->n_n) {
-    if (in->n_n > c->nn_cap) {
-      if (c->d_nread) cudaFree(c->d_nread); if (c->d_npos) cudaFree(c->d_npos);
-      c->nn_cap = in->n_n * 5 / 4 + 64;
-      CK(cudaMalloc((void **)&c->d_nread, c->nn_cap * 4));
-      CK(cudaMalloc((void **)&c->d_npos, c->nn_cap * 4));
-    }
-    CK(cudaMemcpyAsync(c->d_nread, in->n_read, in->n_n * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_npos, in->n_pos, in->n_n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(S.d_nread, in->n_read, in->n_n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(S.d_npos, in->n_pos, in->n_n * 4, cudaMemcpyHostToDevice, st));
   }
-  CK(cudaMemsetAsync(dst.flags, 0, (size_t)(n + 1) * 8, c->stream));
-  CK(cudaStreamSynchronize(c->stream));                  // host vectors woff/pbase go out of scope
-  if (upload_ms) *upload_ms = tu.stop(); else tu.stop();
-
-  EvTimer te(c->stream);
+  CK(cudaMemsetAsync(dst.flags, 0, (size_t)(n + 1) * 8, st));
+  if (is_hash) CK(cudaEventRecord(e1, st));
   if (n) {
-    k_encode_fwd<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(c->d_packed, c->d_boff, dst.len, dst.woff, dst.fwd, n); c->launches++;
-    if (in->n_n) { k_apply_n<<<div_up(in->n_n, 256), 256, 0, c->stream>>>(c->d_nread, c->d_npos, in->n_n, dst.woff, dst.len, dst.fwd); c->launches++; }
-    k_encode_rc<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(dst.fwd, dst.len, dst.woff, dst.rc, n); c->launches++;
+    k_encode_fwd<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(S.d_packed, S.d_boff, dst.len, dst.woff, dst.fwd, n); c->launches++;
+    if (in->n_n) { k_apply_n<<<div_up(in->n_n, 256), 256, 0, st>>>(S.d_nread, S.d_npos, in->n_n, dst.woff, dst.len, dst.fwd); c->launches++; }
+    k_encode_rc<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(dst.fwd, dst.len, dst.woff, dst.rc, n); c->launches++;
   }
   CK(cudaGetLastError());
-  if (encode_ms) *encode_ms = te.stop(); else te.stop();
+  if (is_hash) {
+    CK(cudaEventRecord(e2, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1); if (upload_ms) *upload_ms = ms;
+    cudaEventElapsedTime(&ms, e1, e2); if (encode_ms) *encode_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  } else {
+    CK(cudaEventRecord(c->ref_up1, st));
+    CK(cudaEventRecord(c->ref_ready, st));
+    c->ref_pending = true;
+  }
   (void)is_hash;
   return OVLB_OK;
 }

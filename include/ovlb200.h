@@ -157,8 +157,12 @@ int  ovlb_build_index(ovlb_ctx *ctx);
 int  ovlb_overlap_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads,
                             ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
 
-/*  Same, but for benchmarking with inputs resident in HBM: stage a batch once,
- *  then run the device pipeline repeatedly without host<->device copies.  */
+/*  The same in three steps.  ovlb_stage_ref_batch uploads and encodes the batch on the context's COPY stream and
+ *  returns without waiting when the caller's buffers are page-locked (ovlb_host_register): it may be called before
+ *  ovlb_build_index, so that the upload of the ref batch overlaps the index build, and the buffers it was given must
+ *  stay valid and unchanged until ovlb_run_staged returns.  ovlb_run_staged waits for the upload, runs the device
+ *  pipeline (it can be repeated on the staged batch: benchmarking with inputs resident in HBM) and
+ *  ovlb_fetch_records copies the records out.  */
 int  ovlb_stage_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads);
 int  ovlb_run_staged(ovlb_ctx *ctx, uint64_t *n_records);
 int  ovlb_fetch_records(ovlb_ctx *ctx, ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
