@@ -775,24 +775,38 @@ __device__ __forceinline__ bool head_to_run(const ExpandArgs &A, uint32_t pos, i
   return true;
 }
 
-__device__ __forceinline__ void append_run(const ExpandArgs &A, bool has, uint64_t rkey, uint64_t rval, int lane) {
+//  Runs are staged per warp in shared memory and appended RUN_STAGE at a time: one global atomic per ~100 runs
+//  instead of one per loop iteration (a few million same-address atomics per C2 tile otherwise).
+#define RUN_STAGE 128
+struct RunStage { uint64_t *key, *val; int n; };
+
+__device__ __forceinline__ void run_flush(const ExpandArgs &A, RunStage &S, int lane) {
+  if (S.n == 0) return;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(A.n_runs, (unsigned long long)S.n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncwarp();
+  for (int j = lane; j < S.n; j += 32)
+    if (base + j < A.run_cap) { A.run_key[base + j] = S.key[j]; A.run_val[base + j] = S.val[j]; }
+  __syncwarp();
+  S.n = 0;
+}
+
+__device__ __forceinline__ void append_run(const ExpandArgs &A, RunStage &S, bool has, uint64_t rkey, uint64_t rval, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, has);
   if (!m) return;
-  unsigned long long base = 0;
-  const int leader = __ffs(m) - 1;
-  if (lane == leader) base = atomicAdd(A.n_runs, (unsigned long long)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (has) {
-    const unsigned long long idx = base + __popc(m & ((1u << lane) - 1));
-    if (idx < A.run_cap) { A.run_key[idx] = rkey; A.run_val[idx] = rval; }
-  }
+  if (S.n + 32 > RUN_STAGE) run_flush(A, S, lane);
+  if (has) { const int i = S.n + __popc(m & ((1u << lane) - 1)); S.key[i] = rkey; S.val[i] = rval; }
+  S.n += __popc(m);
 }
 
 //  thread per item, items of at most SMALL_ITEM_MAX occurrences
 __global__ void __launch_bounds__(256)
 k_expand_small(ExpandArgs A, const uint4 *__restrict__ items, const unsigned long long *n_items_p, uint64_t item_cap,
                unsigned long long *counters) {
+  __shared__ uint64_t st_key[8][RUN_STAGE], st_val[8][RUN_STAGE];
   const int lane = threadIdx.x & 31;
+  RunStage S; S.key = st_key[threadIdx.x >> 5]; S.val = st_val[threadIdx.x >> 5]; S.n = 0;
   unsigned long long n_items = *n_items_p; if (n_items > item_cap) n_items = item_cap;
   unsigned long long hits = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -807,9 +821,10 @@ k_expand_small(ExpandArgs A, const uint4 *__restrict__ items, const unsigned lon
       bool has = false;
       if (j < cnt) has = head_to_run(A, it.x, dir, A.occ[it.y + j], rk, rv, rl);
       if (has) hits += rl;
-      append_run(A, has, rk, rv, lane);
+      append_run(A, S, has, rk, rv, lane);
     }
   }
+  run_flush(A, S, lane);
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
   if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
@@ -819,7 +834,9 @@ k_expand_small(ExpandArgs A, const uint4 *__restrict__ items, const unsigned lon
 __global__ void __launch_bounds__(256)
 k_expand_large(ExpandArgs A, const uint4 *__restrict__ items, const unsigned long long *n_items_p, uint64_t item_cap,
                unsigned long long *counters) {
+  __shared__ uint64_t st_key[8][RUN_STAGE], st_val[8][RUN_STAGE];
   const int lane = threadIdx.x & 31;
+  RunStage S; S.key = st_key[threadIdx.x >> 5]; S.val = st_val[threadIdx.x >> 5]; S.n = 0;
   unsigned long long n_items = *n_items_p; if (n_items > item_cap) n_items = item_cap;
   unsigned long long hits = 0;
   const uint64_t wstride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -832,9 +849,10 @@ k_expand_large(ExpandArgs A, const uint4 *__restrict__ items, const unsigned lon
       bool has = false;
       if (j < cnt) has = head_to_run(A, it.x, dir, A.occ[it.y + j], rk, rv, rl);
       if (has) hits += rl;
-      append_run(A, has, rk, rv, lane);
+      append_run(A, S, has, rk, rv, lane);
     }
   }
+  run_flush(A, S, lane);
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) hits += __shfl_down_sync(0xffffffffu, hits, o);
   if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
