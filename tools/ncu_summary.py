@@ -35,7 +35,7 @@ def main():
         hdr = None; fname = ''
         acc = collections.OrderedDict()
         for r in rows:
-            if r and r[0] == 'File Name':
+            if r and r[0] in ('File Name', 'File Path'):
                 fname = r[1].split('/')[-1]; continue
             if r and r[0] == 'Line No':
                 hdr = r; continue
@@ -48,6 +48,7 @@ def main():
             try: inst = int(d.get('Instructions Executed', '0') or 0)
             except ValueError: inst = 0
             if samp == 0 and inst == 0: continue
+            if not d.get('Line No', '').strip(): continue          # SASS rows under a source line: already counted in it
             stalls = {k[6:]: int(v) for k, v in d.items() if k.startswith('stall_') and '(' not in k and v.isdigit() and int(v) > 0}
             key = (fname, d['Line No'], d['Source'].strip()[:100])
             a = acc.setdefault(key, [0, 0, collections.Counter()])
