@@ -76,7 +76,7 @@ EXPORTS = [
     "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
-    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info",
+    "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
     "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_assign_tiles",
 ]
@@ -115,6 +115,7 @@ def load_library():
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
     L.ovlb_debug_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_params_init.argtypes = [C.POINTER(_Params), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.ovlb_params_free.argtypes = [C.POINTER(_Params)]
@@ -325,6 +326,14 @@ class Overlapper:
         ms = C.c_float()
         _check(self.L.ovlb_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def ingest_records(self, recs: np.ndarray, max_evalue: int, max_id: int) -> np.ndarray:
+        """Mirror + filter + sort overlap records the way the overlap-store build does (ovlb_ingest_records)."""
+        recs = np.ascontiguousarray(recs, dtype=RECORD_DTYPE)
+        out = np.zeros(max(2 * recs.size, 1), dtype=RECORD_DTYPE)
+        n = C.c_uint64()
+        _check(self.L.ovlb_ingest_records(self._h, recs.ctypes.data, recs.size, max_evalue, max_id, out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value]
 
     # --- debug taps (tests) ---
     def debug_index_info(self) -> dict:

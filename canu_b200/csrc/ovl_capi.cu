@@ -12,6 +12,8 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
 int ovl_build_index(ovlb_ctx *c);
 int ovl_seed_ref_batch(ovlb_ctx *c);
 int ovl_extend_pairs(ovlb_ctx *c);
+int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
+                       ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
 int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
                      const int32_t *seed_start, const int32_t *seed_offset, const int32_t *seed_len,
                      int32_t *out7, int32_t *deltas, uint32_t delta_stride);
@@ -285,6 +287,13 @@ int ovlb_timer_stop(ovlb_ctx *c, float *ms) {
   CK(cudaEventSynchronize(c->ev_stop));
   CK(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
   return OVLB_OK;
+}
+
+int ovlb_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
+                        ovlb_record *out, uint64_t out_cap, uint64_t *n_out) {
+  if (!c || !n_out || (n && (!in || !out))) { ovl_set_error("ovlb_ingest_records: null argument"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  return ovl_ingest_records(c, in, n, max_evalue, max_id, out, out_cap, n_out);
 }
 
 int ovlb_debug_index_info(ovlb_ctx *c, uint64_t out[4]) {

@@ -1,0 +1,127 @@
+//  ovl_ingest.cu -- the step right after the overlapper: what Canu's overlap-store build does to
+//  every record before it is written -- mirror, filter, sort -- on the GPU, so that an overlapper running on the device
+//  can hand the store pre-mirrored, pre-sorted slices instead of feeding a disk-bound bucket sort.
+//
+//  Replaces, bit-exactly (paths under /root/reference/src/stores):
+//    ovStoreFilter::filterOverlap        ovStoreFilter.C:71-150   ID range check, mirrored twin, error-rate filter
+//    ovOverlap::swapIDs                  ovOverlap.C:215-246      hang swap (and 5'/3' reversal for flipped overlaps)
+//    std::sort + ovOverlap::operator<    ovStoreBuild.C:252, ovStoreSorter.C:223, ovOverlap.H:265-279
+//
+//  Byte/integer work, HBM-bound: one pass that writes both twins with a 64-bit (a_iid, b_iid) key, a radix sort of
+//  (key, index), a gather, and a fix-up of the rare equal-(a, b) runs by (dat0, dat1).
+#include "ovl_ctx.h"
+
+#include <cub/cub.cuh>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ovl_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return OVLB_ERR_CUDA; } } while (0)
+
+static inline unsigned div_up64(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+#define ING_M21    ((1ull << 21) - 1)
+#define ING_FLAGS  (7ull << 59)                    // forOBT (59) | forDUP (60) | forUTG (61)
+#define ING_DROP   0xFFFFFFFFFFFFFFFFull           // key of a record that no longer carries a flag (a_iid is never 2^32-1 ... and b)
+
+//  one thread per input record: both twins -> tmp[2i], tmp[2i+1] with their sort keys; out[0] += kept, out[1] |= bad IDs
+__global__ void __launch_bounds__(256)
+k_ingest_mirror(const ovlb_record *__restrict__ in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
+                ovlb_record *__restrict__ tmp, uint64_t *__restrict__ key, uint32_t *__restrict__ idx, unsigned long long *out) {
+  __shared__ unsigned int blk_kept;
+  if (threadIdx.x == 0) blk_kept = 0;
+  __syncthreads();
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int kept = 0;
+  if (i < n) {
+    const ovlb_record f = in[i];
+    if (f.a_iid == 0 || f.b_iid == 0 || f.a_iid > max_id || f.b_iid > max_id) atomicOr(&out[1], 1ull);
+    uint64_t w0 = f.dat0, w1 = f.dat1;
+    const uint64_t ahg5 = w0 & ING_M21, ahg3 = (w0 >> 21) & ING_M21, bhg5 = w1 & ING_M21, bhg3 = (w1 >> 21) & ING_M21;
+    const bool flipped = (w0 >> 58) & 1ull;
+    const uint32_t evalue = (uint32_t)(w0 >> 42) & 0xFFFFu;
+    if (evalue > max_evalue) w0 &= ~ING_FLAGS;                         // both twins lose their flags
+    const uint64_t hi0 = w0 & ~((1ull << 42) - 1), hi1 = w1 & ~((1ull << 42) - 1);
+    ovlb_record r;
+    r.a_iid = f.b_iid; r.b_iid = f.a_iid;
+    r.dat0 = hi0 | (flipped ? bhg3 : bhg5) | ((flipped ? bhg5 : bhg3) << 21);
+    r.dat1 = hi1 | (flipped ? ahg3 : ahg5) | ((flipped ? ahg5 : ahg3) << 21);
+    ovlb_record ff = f; ff.dat0 = w0;
+    const bool keep = (w0 & ING_FLAGS) != 0;                           // the twin carries the same flags
+    tmp[2 * i] = ff; tmp[2 * i + 1] = r;
+    key[2 * i]     = keep ? (((uint64_t)ff.a_iid << 32) | ff.b_iid) : ING_DROP;
+    key[2 * i + 1] = keep ? (((uint64_t)r.a_iid << 32) | r.b_iid) : ING_DROP;
+    idx[2 * i] = (uint32_t)(2 * i); idx[2 * i + 1] = (uint32_t)(2 * i + 1);
+    kept = keep ? 2u : 0u;
+  }
+  if (kept) atomicAdd(&blk_kept, kept);
+  __syncthreads();
+  if (threadIdx.x == 0 && blk_kept) atomicAdd(&out[0], (unsigned long long)blk_kept);
+}
+
+__global__ void __launch_bounds__(256)
+k_ingest_gather(const ovlb_record *__restrict__ tmp, const uint32_t *__restrict__ order, uint64_t n, ovlb_record *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tmp[order[i]];
+}
+
+//  records with equal (a_iid, b_iid) are adjacent after the sort; order each such run by (dat0, dat1).  One thread per run
+//  head; runs are 1 long except for -m overlaps and duplicated inputs.
+__global__ void __launch_bounds__(256)
+k_ingest_ties(const uint64_t *__restrict__ skey, uint64_t n, ovlb_record *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = skey[i];
+  if (i > 0 && skey[i - 1] == k) return;
+  uint64_t e = i + 1;
+  while (e < n && skey[e] == k) e++;
+  for (uint64_t a = i + 1; a < e; a++) {                               // insertion sort
+    const ovlb_record x = out[a];
+    uint64_t b = a;
+    while (b > i && (out[b - 1].dat0 > x.dat0 || (out[b - 1].dat0 == x.dat0 && out[b - 1].dat1 > x.dat1))) { out[b] = out[b - 1]; b--; }
+    out[b] = x;
+  }
+}
+
+int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
+                       ovlb_record *out, uint64_t out_cap, uint64_t *n_out) {
+  *n_out = 0;
+  if (n == 0) return OVLB_OK;
+  if (2 * n >= 0xFFFFFFF0ull) { ovl_set_error("ovlb_ingest_records: more than 2^31 records in one call; split the input"); return OVLB_ERR_CAPACITY; }
+  const uint64_t m = 2 * n;
+  ovlb_record *d_in = nullptr, *d_tmp = nullptr, *d_out = nullptr;
+  uint64_t *d_key = nullptr, *d_key2 = nullptr; uint32_t *d_idx = nullptr, *d_idx2 = nullptr; void *d_cub = nullptr;
+  auto cleanup = [&]() { void *p[] = { d_in, d_tmp, d_out, d_key, d_key2, d_idx, d_idx2, d_cub }; for (void *q : p) if (q) cudaFree(q); };
+#define CKF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ovl_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); cleanup(); return OVLB_ERR_CUDA; } } while (0)
+  CKF(cudaMalloc((void **)&d_in, n * sizeof(ovlb_record)));
+  CKF(cudaMalloc((void **)&d_tmp, m * sizeof(ovlb_record)));
+  CKF(cudaMalloc((void **)&d_key, m * 8)); CKF(cudaMalloc((void **)&d_key2, m * 8));
+  CKF(cudaMalloc((void **)&d_idx, m * 4)); CKF(cudaMalloc((void **)&d_idx2, m * 4));
+  CKF(cudaMemcpyAsync(d_in, in, n * sizeof(ovlb_record), cudaMemcpyHostToDevice, c->stream));
+  CKF(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
+  k_ingest_mirror<<<div_up64(n, 256), 256, 0, c->stream>>>(d_in, n, max_evalue, max_id, d_tmp, d_key, d_idx, &c->d_work[5]);
+  c->launches++;
+  int end_bit = 33; { uint32_t x = max_id; while (x >>= 1) end_bit++; } if (end_bit > 64) end_bit = 64;
+  end_bit = 64;                                                        // dropped records carry the all-ones key
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, end_bit, c->stream);
+  CKF(cudaMalloc(&d_cub, tb + 256));
+  CKF(cub::DeviceRadixSort::SortPairs(d_cub, tb, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, end_bit, c->stream));
+  c->launches += 10;
+  unsigned long long h[2] = {0, 0};
+  CKF(cudaMemcpyAsync(h, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
+  CKF(cudaStreamSynchronize(c->stream));
+  if (h[1]) { ovl_set_error("ovlb_ingest_records: Overlap has IDs out of range (maxID " + std::to_string(max_id) + "), possibly corrupt input data."); cleanup(); return OVLB_ERR_ARG; }
+  const uint64_t kept = h[0];
+  *n_out = kept;
+  if (kept > out_cap) { ovl_set_error("ovlb_ingest_records: output buffer too small"); cleanup(); return OVLB_ERR_CAPACITY; }
+  if (kept) {
+    CKF(cudaMalloc((void **)&d_out, kept * sizeof(ovlb_record)));
+    k_ingest_gather<<<div_up64(kept, 256), 256, 0, c->stream>>>(d_tmp, d_idx2, kept, d_out);
+    k_ingest_ties<<<div_up64(kept, 256), 256, 0, c->stream>>>(d_key2, kept, d_out);
+    c->launches += 2;
+    CKF(cudaMemcpyAsync(out, d_out, kept * sizeof(ovlb_record), cudaMemcpyDeviceToHost, c->stream));
+    CKF(cudaStreamSynchronize(c->stream));
+  }
+  CKF(cudaGetLastError());
+  cleanup();
+#undef CKF
+  return OVLB_OK;
+}

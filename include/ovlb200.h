@@ -266,6 +266,16 @@ int  ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ol
 /*  owner[i] in [0, n_workers): longest-processing-time-first on tiles[i].cost, deterministic.  */
 int  ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner);
 
+/*  The store-ingest step that follows the overlapper: what ovStoreBuild / ovStoreBucketizer +
+ *  ovStoreSorter do to every record before writing it.  For each input record the mirrored twin is made
+ *  (ovOverlap::swapIDs, stores/ovOverlap.C:215-246), records whose evalue exceeds max_evalue lose their
+ *  forUTG/forOBT/forDUP flags and are dropped with their twin (ovStoreFilter::filterOverlap,
+ *  stores/ovStoreFilter.C:71-150), and the survivors are sorted by (a_iid, b_iid, dat0, dat1)
+ *  (ovOverlap::operator<, stores/ovOverlap.H:265-279).  An ID outside 1..max_id fails the call with OVLB_ERR_ARG
+ *  (the reference exits).  out must hold up to 2 * n records; host buffers.  */
+int  ovlb_ingest_records(ovlb_ctx *ctx, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
+                         ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -304,3 +304,70 @@ def test_index_build_paths_agree_and_overflow_falls_back():
     unit = rep[step // 3: step // 3 + 300]
     info = run(rep, unit)
     assert not info["bucketed"], info                  # ~9000 occurrences of every repeat k-mer: a bucket overflowed
+
+
+# ------------------------------------------------------------------------------------------------
+#  store-ingest step: ovlb_ingest_records vs the reference-minted goldens and the numpy oracle
+# ------------------------------------------------------------------------------------------------
+def _ingest_cases():
+    import json
+    import os
+    return json.load(open(os.path.join(gu.GOLDEN, "ingest.json")))
+
+
+@pytest.mark.parametrize("case", _ingest_cases(), ids=[c["golden"] for c in _ingest_cases()])
+def test_ingest_matches_reference_goldens(case):
+    import gzip
+    import os
+    import subprocess
+    from oracle import ingest_oracle as io_
+    api = _api()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lines = subprocess.check_output([os.path.join(root, "canu_b200", "bin", "ovltool"), "dump-ovb",
+                                     os.path.join(gu.GOLDEN, case["input"])]).decode().splitlines()
+    recs = np.zeros(len(lines), dtype=api.RECORD_DTYPE)
+    for i, ln in enumerate(lines):
+        x = ln.split()
+        recs[i] = (int(x[0]), int(x[1]), int(x[2], 16), int(x[3], 16))
+    with gzip.open(os.path.join(gu.GOLDEN, case["golden"]), "rb") as f:
+        want = np.frombuffer(f.read(), dtype=api.RECORD_DTYPE)
+    ov = api.Overlapper(api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500))
+    got = ov.ingest_records(recs, io_.encode_evalue(case["max_erate"]), gu.load_cases()["stores"]["A"]["reads"])
+    ov.close()
+    assert len(got) == len(want) == case["records"]
+    for f in ("a_iid", "b_iid", "w0", "w1"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+def test_ingest_random_records_ties_and_edges():
+    """Two million random records (both orientations, all flag patterns, runs of equal (a, b) with different payloads)
+    against the numpy oracle; sortedness and the mirror property checked on the result itself; empty input; everything
+    filtered; an ID out of range fails like the reference."""
+    from oracle import ingest_oracle as io_
+    api = _api()
+    rng = np.random.default_rng(5)
+    n, max_id = 2_000_000, 300_000
+    recs = np.zeros(n, dtype=api.RECORD_DTYPE)
+    recs["a_iid"] = rng.integers(1, max_id + 1, n)
+    recs["b_iid"] = rng.integers(1, max_id + 1, n)
+    recs["a_iid"][: n // 50] = recs["a_iid"][n // 50: 2 * (n // 50)]          # repeated (a, b): ties resolved by the payload
+    recs["b_iid"][: n // 50] = recs["b_iid"][n // 50: 2 * (n // 50)]
+    h = lambda: rng.integers(0, 1 << 21, n, dtype=np.uint64)
+    flags = rng.integers(0, 16, n, dtype=np.uint64)                          # flipped | obt | dup | utg
+    recs["w0"] = h() | (h() << np.uint64(21)) | (rng.integers(0, 6000, n, dtype=np.uint64) << np.uint64(42)) | (flags << np.uint64(58))
+    recs["w1"] = h() | (h() << np.uint64(21)) | (h() << np.uint64(42))
+    ov = api.Overlapper(api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500))
+    got = ov.ingest_records(recs, 4500, max_id)
+    want = io_.ingest(recs, 4500, max_id)
+    assert len(got) == len(want) and len(got) > n
+    for f in ("a_iid", "b_iid", "w0", "w1"):
+        assert np.array_equal(got[f], want[f]), f
+    k = (got["a_iid"].astype(np.uint64) << np.uint64(32)) | got["b_iid"]
+    assert np.all(k[1:] >= k[:-1])
+    assert len(ov.ingest_records(recs[:0], 4500, max_id)) == 0
+    assert len(ov.ingest_records(recs[:1000], 0, max_id)) == int(2 * np.sum(((recs["w0"][:1000] >> np.uint64(42)) & np.uint64(0xFFFF) == 0) &
+                                                                            ((recs["w0"][:1000] >> np.uint64(59)) & np.uint64(7) != 0)))
+    bad = recs[:10].copy(); bad["b_iid"][3] = max_id + 1
+    with pytest.raises(api.OvlError):
+        ov.ingest_records(bad, 4500, max_id)
+    ov.close()
