@@ -7,8 +7,9 @@
 //    ovOverlap::swapIDs                  ovOverlap.C:215-246      hang swap (and 5'/3' reversal for flipped overlaps)
 //    std::sort + ovOverlap::operator<    ovStoreBuild.C:252, ovStoreSorter.C:223, ovOverlap.H:265-279
 //
-//  Byte/integer work, HBM-bound: one pass that writes both twins with a 64-bit (a_iid, b_iid) key, a radix sort of
-//  (key, index), a gather, and a fix-up of the rare equal-(a, b) runs by (dat0, dat1).
+//  Byte/integer work, HBM-bound: one pass writes both twins, then a least-significant-key-first sequence of three stable
+//  64-bit radix sorts of (key, index) -- dat1, dat0, (a_iid, b_iid) -- gives the reference's full 192-bit order whatever
+//  the number of records that share an (a, b) pair, and one gather writes the records out.
 #include "ovl_ctx.h"
 
 #include <cub/cub.cuh>
@@ -24,7 +25,7 @@ static inline unsigned div_up64(uint64_t a, uint64_t b) { return (unsigned)((a +
 //  one thread per input record: both twins -> tmp[2i], tmp[2i+1] with their sort keys; out[0] += kept, out[1] |= bad IDs
 __global__ void __launch_bounds__(256)
 k_ingest_mirror(const ovlb_record *__restrict__ in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
-                ovlb_record *__restrict__ tmp, uint64_t *__restrict__ key, uint32_t *__restrict__ idx, unsigned long long *out) {
+                ovlb_record *__restrict__ tmp, uint32_t *__restrict__ idx, unsigned long long *out) {
   __shared__ unsigned int blk_kept;
   if (threadIdx.x == 0) blk_kept = 0;
   __syncthreads();
@@ -46,8 +47,6 @@ k_ingest_mirror(const ovlb_record *__restrict__ in, uint64_t n, uint32_t max_eva
     ovlb_record ff = f; ff.dat0 = w0;
     const bool keep = (w0 & ING_FLAGS) != 0;                           // the twin carries the same flags
     tmp[2 * i] = ff; tmp[2 * i + 1] = r;
-    key[2 * i]     = keep ? (((uint64_t)ff.a_iid << 32) | ff.b_iid) : ING_DROP;
-    key[2 * i + 1] = keep ? (((uint64_t)r.a_iid << 32) | r.b_iid) : ING_DROP;
     idx[2 * i] = (uint32_t)(2 * i); idx[2 * i + 1] = (uint32_t)(2 * i + 1);
     kept = keep ? 2u : 0u;
   }
@@ -62,22 +61,13 @@ k_ingest_gather(const ovlb_record *__restrict__ tmp, const uint32_t *__restrict_
   if (i < n) out[i] = tmp[order[i]];
 }
 
-//  records with equal (a_iid, b_iid) are adjacent after the sort; order each such run by (dat0, dat1).  One thread per run
-//  head; runs are 1 long except for -m overlaps and duplicated inputs.
+//  sort key `which` (0: dat1, 1: dat0, 2: a_iid << 32 | b_iid, all-ones for a record without flags) of record perm[i]
 __global__ void __launch_bounds__(256)
-k_ingest_ties(const uint64_t *__restrict__ skey, uint64_t n, ovlb_record *out) {
+k_ingest_key(const ovlb_record *__restrict__ tmp, const uint32_t *__restrict__ perm, uint64_t n, int which, uint64_t *__restrict__ key) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t k = skey[i];
-  if (i > 0 && skey[i - 1] == k) return;
-  uint64_t e = i + 1;
-  while (e < n && skey[e] == k) e++;
-  for (uint64_t a = i + 1; a < e; a++) {                               // insertion sort
-    const ovlb_record x = out[a];
-    uint64_t b = a;
-    while (b > i && (out[b - 1].dat0 > x.dat0 || (out[b - 1].dat0 == x.dat0 && out[b - 1].dat1 > x.dat1))) { out[b] = out[b - 1]; b--; }
-    out[b] = x;
-  }
+  const ovlb_record r = tmp[perm[i]];
+  key[i] = which == 0 ? r.dat1 : which == 1 ? r.dat0 : ((r.dat0 & ING_FLAGS) ? (((uint64_t)r.a_iid << 32) | r.b_iid) : ING_DROP);
 }
 
 int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
@@ -96,15 +86,18 @@ int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t 
   CKF(cudaMalloc((void **)&d_idx, m * 4)); CKF(cudaMalloc((void **)&d_idx2, m * 4));
   CKF(cudaMemcpyAsync(d_in, in, n * sizeof(ovlb_record), cudaMemcpyHostToDevice, c->stream));
   CKF(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
-  k_ingest_mirror<<<div_up64(n, 256), 256, 0, c->stream>>>(d_in, n, max_evalue, max_id, d_tmp, d_key, d_idx, &c->d_work[5]);
+  k_ingest_mirror<<<div_up64(n, 256), 256, 0, c->stream>>>(d_in, n, max_evalue, max_id, d_tmp, d_idx, &c->d_work[5]);
   c->launches++;
-  int end_bit = 33; { uint32_t x = max_id; while (x >>= 1) end_bit++; } if (end_bit > 64) end_bit = 64;
-  end_bit = 64;                                                        // dropped records carry the all-ones key
   size_t tb = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, end_bit, c->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, 64, c->stream);
   CKF(cudaMalloc(&d_cub, tb + 256));
-  CKF(cub::DeviceRadixSort::SortPairs(d_cub, tb, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, end_bit, c->stream));
-  c->launches += 10;
+  for (int which = 0; which < 3; which++) {                             // least significant key first; every sort is stable
+    k_ingest_key<<<div_up64(m, 256), 256, 0, c->stream>>>(d_tmp, d_idx, m, which, d_key);
+    size_t tb2 = tb;
+    CKF(cub::DeviceRadixSort::SortPairs(d_cub, tb2, d_key, d_key2, d_idx, d_idx2, (int64_t)m, 0, 64, c->stream));
+    std::swap(d_idx, d_idx2);
+    c->launches += 11;
+  }
   unsigned long long h[2] = {0, 0};
   CKF(cudaMemcpyAsync(h, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
   CKF(cudaStreamSynchronize(c->stream));
@@ -114,9 +107,8 @@ int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t 
   if (kept > out_cap) { ovl_set_error("ovlb_ingest_records: output buffer too small"); cleanup(); return OVLB_ERR_CAPACITY; }
   if (kept) {
     CKF(cudaMalloc((void **)&d_out, kept * sizeof(ovlb_record)));
-    k_ingest_gather<<<div_up64(kept, 256), 256, 0, c->stream>>>(d_tmp, d_idx2, kept, d_out);
-    k_ingest_ties<<<div_up64(kept, 256), 256, 0, c->stream>>>(d_key2, kept, d_out);
-    c->launches += 2;
+    k_ingest_gather<<<div_up64(kept, 256), 256, 0, c->stream>>>(d_tmp, d_idx, kept, d_out);
+    c->launches++;
     CKF(cudaMemcpyAsync(out, d_out, kept * sizeof(ovlb_record), cudaMemcpyDeviceToHost, c->stream));
     CKF(cudaStreamSynchronize(c->stream));
   }

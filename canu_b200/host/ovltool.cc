@@ -85,6 +85,19 @@ int main(int argc, char **argv) {
     if (!W.close(err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     return 0;
   }
+  if (argc >= 5 && !strcmp(argv[1], "pack-ovb")) {                     // flat {u32 a, u32 b, u64 dat0, u64 dat1} records -> .ovb + .oc
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    OvFileWriter W;
+    if (!W.open(argv[3], (uint32_t)strtoul(argv[4], nullptr, 10), err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    std::vector<ovlb_record> buf(1 << 20);
+    size_t got;
+    while ((got = fread(buf.data(), sizeof(ovlb_record), buf.size(), f)) > 0)
+      W.submit(std::vector<ovlb_record>(buf.begin(), buf.begin() + got));
+    fclose(f);
+    if (!W.close(err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    return 0;
+  }
   if (argc >= 4 && !strcmp(argv[1], "cmp-ovb")) {
     //  canonical-sort both files (ovOverlap::operator<, stores/ovOverlap.H:263-276) and compare record by record;
     //  optional 4th argument: a read ID whose records are ignored on both sides (the reference's last-ref-read quirk)
@@ -118,6 +131,6 @@ int main(int argc, char **argv) {
     printf("first %zu second %zu only-first %zu only-second %zu\n", A.size(), B.size(), onlyA, onlyB);
     return (onlyA || onlyB) ? 1 : 0;
   }
-  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
+  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
   return 1;
 }
