@@ -2,16 +2,23 @@
 //
 //  Kernels (SURVEY.md 2.1 numbering):
 //    K0  encode_fwd / apply_n / encode_rc       sqStore 2-bit bytes -> dp4 words, both orientations
-//    K1  index_count / index_fill               Build_Hash_Index + Put_String_In_Hash + Hash_Insert
-//                                               (overlapInCore-Build_Hash_Index.C:267-404,415-631)
+//    K1  hash_tuples_compact -> radix partition -> bucket_group -> path sort -> path_slots
+//                                               Build_Hash_Index + Put_String_In_Hash + Hash_Insert + chain coalescing
+//                                               (overlapInCore-Build_Hash_Index.C:267-404,415-631): one 32-byte slot per
+//                                               distinct k-mer in PATH order, class-partitioned occurrence lists, a
+//                                               hash table k-mer -> slot.  Fallback (a bucket that does not fit shared
+//                                               memory): hash_tuples -> full radix sort -> count_distinct -> group_heads
 //    K1b index_skip                             Mark_Skip_Kmers / Hash_Mark_Empty / Mark_Screened_Ends (:98-257)
-//    K2a ref_probe                              Find_Overlaps window loop + Hash_Find (Find_Overlaps.C:177-336)
-//    K2b ref_expand                             chain walk + Add_Ref, collapsed to maximal diagonal runs
-//    K3  pair_heads / runs_unpack / chain_pairs Add_Match replay, hopeless check, --minkmers filter
-//                                               (Find_Overlaps.C:26-163, Process_String_Overlaps.C:384-415,581-637)
+//    K2a ref_probe                              Find_Overlaps window loop + Hash_Find (Find_Overlaps.C:177-336):
+//                                               speculative coalesced slot loads along the path, hash table at breaks
+//    K2b expand_small / expand_large            chain walk + Add_Ref, collapsed to maximal diagonal runs
+//    K3  pair_heads / pair_scatter / chain_pairs / pair_cost
+//                                               Add_Match replay, hopeless check, --minkmers filter
+//                                               (Find_Overlaps.C:26-163, Process_String_Overlaps.C:384-415,581-637),
+//                                               heaviest-first order of the pairs for the extension kernel
 //
-//  All HBM-bound integer work: coalesced streaming of dp4 words and position arrays, random 8/16-byte
-//  probes into the open-addressed table, warp-aggregated appends.  No tensor cores.
+//  All integer / byte work: coalesced streaming of dp4 words and tuples, shared-memory grouping, 32-byte slot loads,
+//  warp- and block-aggregated appends.  No tensor cores.
 #include "ovl_ctx.h"
 
 #include <cub/cub.cuh>

@@ -231,7 +231,7 @@ def test_drop_in_executable_on_sqstore(case, build_env, tmp_path):
 
 @pytest.mark.parametrize("extra", [["--gpus", "0,0", "--hashblock", "250000", "--refbatch", "120000"],
                                    ["--gpus", "0,0,0", "--hashblock", "60000", "--refbatch", "400000"],
-                                   ["--gpus", "all"]])
+                                   ["--gpus", "all"], ["--gpu", "0", "--streams", "2", "--refbatch", "300000"]])
 def test_drop_in_executable_multi_worker(extra, tmp_path):
     """The multi-GPU path of the host driver (tile plan -> LPT owners -> one worker thread and context per
     device -> one writer): with a device listed several times the same code runs on a one-GPU box.  Output must
