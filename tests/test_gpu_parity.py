@@ -371,3 +371,32 @@ def test_ingest_random_records_ties_and_edges():
     with pytest.raises(api.OvlError):
         ov.ingest_records(bad, 4500, max_id)
     ov.close()
+
+
+@pytest.mark.parametrize("K", [17, 28])
+def test_other_kmer_lengths_through_the_bucketed_build(K):
+    """The index build mixes and buckets the k-mer inside its 2K+3 key bits: check a short and a long K against the
+    oracle on a block large enough for the bucketed build."""
+    from oracle import oracle_py as op
+    from canu_b200 import synth
+    api = _api()
+    g = synth.make_genome(60000, seed=90 + K)
+    reads = synth.simulate_reads(g, 12, 1500, 4000, 0.01, seed=91 + K)
+    prm = api.OverlapParams(kmer_len=K, max_erate=0.045, min_olap_len=500, max_read_len=max(r.size for r in reads))
+    ov = api.Overlapper(prm)
+    pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+    ov.load_hash_reads(pk)
+    ov.build_index()
+    assert ov.debug_index_info()["bucketed"]
+    recs = ov.overlap_ref_batch(pk, cap=1 << 20)
+    ctr = ov.counters()
+    ov.close()
+    o = op.Oracle(kmer_len=K, max_erate=0.045, min_olap_len=500, hash_bits=18, hash_load=0.8)
+    o.set_reads(reads)
+    want = op.sort_records(o.run(threads=8))
+    got = np.sort(recs, order=["a_iid", "b_iid", "w0", "w1"])
+    assert len(got) == len(want) and len(got) > 0
+    for f in ("a_iid", "b_iid", "w0", "w1"):
+        assert np.array_equal(got[f], want[f]), f
+    st = o.stats()
+    assert ctr["kmer_hits_with_olap"] == st["kmer_hits_with_olap"] and ctr["kmer_hits_without_olap"] == st["kmer_hits_without_olap"]
