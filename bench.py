@@ -318,7 +318,7 @@ def main():
             finally:
                 shutil.rmtree(wd, ignore_errors=True)
 
-    tt = torch.tensor([dev_ms / args.steps, e2e_wall * 1e3 / args.steps, pairs_step, cells_step], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dev_ms / args.steps, e2e_wall * 1e3 / args.steps, pairs_step, cells_step, h2d, d2h], dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = tt.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -326,6 +326,7 @@ def main():
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_step, e2e_ms = tmax[0].item(), tmax[1].item()
         pairs_all, cells_all = tsum[2].item(), tsum[3].item()
+        h2d, d2h = int(tsum[4].item()), int(tsum[5].item())        # whole job, like `value`
     else:
         ms_step, e2e_ms, pairs_all, cells_all = tt[0].item(), tt[1].item(), pairs_step, cells_step
 
