@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <string>
@@ -134,6 +137,56 @@ static bool pack_range(SqStore &S, uint32_t bgn, uint32_t end, uint32_t min_lib,
   P.view.n_read = P.n_read.data(); P.view.n_pos = P.n_pos.data(); P.view.n_n = P.n_read.size();
   return true;
 }
+
+//  Packs the read ranges a worker is going to need, in order, on a thread of its own and a few items ahead: reading
+//  and packing a batch from the sqStore costs about as much host time as the GPU needs for it on HiFi-like reads, and
+//  the first batches are packed while the CUDA context is still being created.
+struct PackItem { bool is_hash; uint32_t bgn, end; };
+class Prefetcher {
+ public:
+  Prefetcher(const char *store_path, std::vector<PackItem> plan, uint32_t minLibH, uint32_t maxLibH, uint32_t minLibR, uint32_t maxLibR,
+             uint32_t min_len, size_t depth)
+      : path_(store_path), plan_(std::move(plan)), lib_{minLibH, maxLibH, minLibR, maxLibR}, min_len_(min_len), depth_(depth) {
+    th_ = std::thread([this] { run(); });
+  }
+  ~Prefetcher() { { std::lock_guard<std::mutex> lk(mu_); stop_ = true; } cv_.notify_all(); if (th_.joinable()) th_.join(); }
+  //  next item of the plan; nullptr + err on failure
+  std::unique_ptr<Packed> next(std::string &err) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [this] { return !q_.empty() || done_; });
+    if (q_.empty()) { err = err_.empty() ? "prefetcher: plan exhausted" : err_; return nullptr; }
+    std::unique_ptr<Packed> p = std::move(q_.front()); q_.pop_front();
+    lk.unlock(); cv_.notify_all();
+    return p;
+  }
+
+ private:
+  void run() {
+    SqStore st; std::string err;
+    if (!st.open(path_.c_str(), err)) { fail(err); return; }
+    for (const PackItem &it : plan_) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return q_.size() < depth_ || stop_; });
+        if (stop_) break;
+      }
+      std::unique_ptr<Packed> p(new Packed());
+      const bool ok = it.is_hash ? pack_range(st, it.bgn, it.end, lib_[0], lib_[1], min_len_, *p, err)
+                                 : pack_range(st, it.bgn, it.end, lib_[2], lib_[3], min_len_, *p, err);
+      if (!ok) { fail(err); return; }
+      { std::lock_guard<std::mutex> lk(mu_); q_.push_back(std::move(p)); }
+      cv_.notify_all();
+    }
+    { std::lock_guard<std::mutex> lk(mu_); done_ = true; }
+    cv_.notify_all();
+  }
+  void fail(const std::string &e) { { std::lock_guard<std::mutex> lk(mu_); err_ = e; done_ = true; } cv_.notify_all(); }
+
+  std::string path_; std::vector<PackItem> plan_; uint32_t lib_[4]; uint32_t min_len_; size_t depth_;
+  std::thread th_; std::mutex mu_; std::condition_variable cv_;
+  std::deque<std::unique_ptr<Packed>> q_;
+  bool stop_ = false, done_ = false; std::string err_;
+};
 
 //  Mark_Skip_Kmers' file format (Build_Hash_Index.C:186-257): one k-mer per line, first whitespace-
 //  delimited word; a line starting with '>' is a header and the NEXT line holds the k-mer.
@@ -349,6 +402,19 @@ int main(int argc, char **argv) {
     ovlb_ctx *ctx = nullptr;
     Phase &ph = phase[wi];
     const double t_worker = now_s();
+    //  what this worker will read, in order: the hash block whenever it changes, then the tile's ref range
+    std::vector<PackItem> plan;
+    {
+      uint32_t hb = 0, he = 0;
+      for (size_t ti = 0; ti < tiles.size(); ti++) {
+        if (owner[ti] != wi) continue;
+        const ovlb_tile &T = tiles[ti];
+        if (T.hash_bgn != hb || T.hash_end != he) { plan.push_back({true, T.hash_bgn, T.hash_end}); hb = T.hash_bgn; he = T.hash_end; }
+        const uint32_t re = std::min(T.ref_end, T.hash_end > 0 ? T.hash_end - 1 : 0);
+        if (T.ref_bgn <= re) plan.push_back({false, T.ref_bgn, re});
+      }
+    }
+    Prefetcher pf(G.storePath, plan, G.minLibToHash, G.maxLibToHash, G.minLibToRef, G.maxLibToRef, minLen, 3);
     double t0 = now_s();
     ovlb_params Pw = P;
     {
@@ -359,7 +425,8 @@ int main(int argc, char **argv) {
     }
     if (ovlb_create(G.gpus[wi], &Pw, &ctx)) { werr[wi] = ovlb_last_error(); return; }
     ph.create += now_s() - t0;
-    Packed HB, RB;
+    std::unique_ptr<Packed> HBp, RBp;
+    Packed RBsplit;                                                     // halves of an overflowed batch are packed here, synchronously
     uint32_t curHb = 0, curHe = 0;
     std::vector<ovlb_record> recs;
     std::vector<std::pair<uint32_t, uint32_t>> todo;                    // ref ranges of the current tile (split on overflow)
@@ -368,7 +435,9 @@ int main(int argc, char **argv) {
       const ovlb_tile &T = tiles[ti];
       if (T.hash_bgn != curHb || T.hash_end != curHe) {
         t0 = now_s();
-        if (!pack_range(st, T.hash_bgn, T.hash_end, G.minLibToHash, G.maxLibToHash, minLen, HB, err)) { werr[wi] = err; break; }
+        HBp = pf.next(err);
+        if (!HBp) { werr[wi] = err; break; }
+        Packed &HB = *HBp;
         ph.pack_hash += now_s() - t0; t0 = now_s();
         { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Build_Hash_Index from %u to %u (%lu bases)\n", phys(G.gpus[wi]), T.hash_bgn, T.hash_end, (unsigned long)HB.bases); }
         if (ovlb_load_hash_reads(ctx, &HB.view) ||
@@ -381,11 +450,15 @@ int main(int argc, char **argv) {
       const uint32_t re = std::min(T.ref_end, T.hash_end > 0 ? T.hash_end - 1 : 0);
       todo.clear();
       if (T.ref_bgn <= re) todo.push_back({T.ref_bgn, re});
+      bool first = true;
       while (!todo.empty() && werr[wi].empty()) {
         const uint32_t rb = todo.back().first, r2 = todo.back().second;
         todo.pop_back();
         t0 = now_s();
-        if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RB, err)) { werr[wi] = err; break; }
+        if (first) { RBp = pf.next(err); if (!RBp) { werr[wi] = err; break; } }
+        else if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RBsplit, err)) { werr[wi] = err; break; }
+        Packed &RB = first ? *RBp : RBsplit;
+        first = false;
         ph.pack_ref += now_s() - t0; t0 = now_s();
         uint64_t n = 0;
         int rc = (r2 - rb + 1 > 200000) ? OVLB_ERR_CAPACITY : ovlb_stage_ref_batch(ctx, &RB.view);
