@@ -113,6 +113,7 @@ struct ovlb_ctx {
   ExtScratch   ext;
   uint64_t     mem_budget = 0;
   int          sm_count = 148;
+  bool         bucket_attr_set = false;   // k_bucket_group's dynamic shared-memory size was raised on this context's device
 
   //  staging
   //  one set per side (0 = hash, 1 = ref): the ref batch is uploaded on `copy_stream` while the index is being built

@@ -851,8 +851,7 @@ int ovl_extend_pairs(ovlb_ctx *c) {
   int blocks = c->ext.n_warps / EXT_WARPS;
   uint64_t need_blocks = (c->n_pairs + EXT_WARPS - 1) / EXT_WARPS;
   if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
-  static int min_blocks = 0;
-  if (!min_blocks) { const char *ev = getenv("OVLB_EXT_BLOCKS"); min_blocks = ev ? atoi(ev) : 4; if (min_blocks < 2 || min_blocks > 4) min_blocks = 4; }
+  static const int min_blocks = [] { const char *ev = getenv("OVLB_EXT_BLOCKS"); const int v = ev ? atoi(ev) : 4; return (v < 2 || v > 4) ? 4 : v; }();
   if ((uint64_t)c->sm_count * min_blocks < (uint64_t)blocks) blocks = c->sm_count * min_blocks;
 #define EXT_LAUNCH(MB) k_extend_pairs<MB><<<blocks, EXT_THREADS, smem, c->stream>>>( \
       c->dp, c->ext, c->pairs, c->pair_order, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \

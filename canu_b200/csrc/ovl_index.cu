@@ -1126,8 +1126,7 @@ int ovl_build_index(ovlb_ctx *c) {
   if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
 
   //  Bucketed build (default) or sorted build (OVLB_BUCKETED=0, or after a bucket overflowed)
-  static int bucketed_env = -1;
-  if (bucketed_env < 0) { const char *ev = getenv("OVLB_BUCKETED"); bucketed_env = ev ? atoi(ev) : 1; }
+  static const int bucketed_env = [] { const char *ev = getenv("OVLB_BUCKETED"); return ev ? atoi(ev) : 1; }();   // thread-safe init
   bool bucketed = bucketed_env != 0;
   const uint64_t mixc = 0x9E3779B97F4A7C15ull;
   uint64_t mix_inv = mixc;                                              // inverse mod 2^64 by Newton iteration
@@ -1180,8 +1179,8 @@ int ovl_build_index(ovlb_ctx *c) {
       if ((rc = ensure(X.gk, X.gk_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
       if ((rc = ensure(X.gv, X.gv_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
       CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
-      static bool attr_set = false;
-      if (!attr_set) { CK(cudaFuncSetAttribute(k_bucket_group, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM)); attr_set = true; }
+      //  per context, not per process: the attribute belongs to the device the context runs on
+      if (!c->bucket_attr_set) { CK(cudaFuncSetAttribute(k_bucket_group, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM)); c->bucket_attr_set = true; }
       k_bucket_group<<<c->sm_count, BK_THREADS, BK_SMEM, c->stream>>>(X.tkey2, X.occ, offs, nb, K, mix_inv, X.tval, X.tmp_slots,
                                                                         (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, X.gv, &c->d_work[5]);
       c->launches++;
