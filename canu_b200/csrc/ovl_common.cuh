@@ -311,3 +311,25 @@ OVL_HD void ovl_output_partial(uint32_t s_id, uint32_t t_id, int dir, const OvlO
   }
   ovl_pack_record(s_id, t_id, ahg5, ahg3, bhg5, bhg3, span, ovl_encode_evalue(o.quality), dir != 0, 1, 1, 0, oa, ob, w0, w1);
 }
+
+//  ---------------------------------------------------------------------------------------------
+//  Store-ingest step (ovl_ingest.cu): the mirrored twin of an overlap and the error-rate filter.
+//  ovOverlap::swapIDs (stores/ovOverlap.C:215-246) + ovStoreFilter::filterOverlap (stores/ovStoreFilter.C:71-150).
+//  In: one record (dat0, dat1).  Out: dat0 of the forward record after the filter, dat0/dat1 of the twin (whose IDs are
+//  the forward record's, swapped); returns 1 if the pair still carries a forUTG/forOBT/forDUP flag (is kept).
+//  Host+device so that tests/model can run the very code the kernel runs.
+//  ---------------------------------------------------------------------------------------------
+#define OVL_ING_M21    ((1ull << 21) - 1)
+#define OVL_ING_FLAGS  (7ull << 59)                    // forOBT (59) | forDUP (60) | forUTG (61)
+
+OVL_HD int ovl_ingest_twin(uint64_t w0, uint64_t w1, uint32_t max_evalue, uint64_t *f0, uint64_t *r0, uint64_t *r1) {
+  const uint64_t ahg5 = w0 & OVL_ING_M21, ahg3 = (w0 >> 21) & OVL_ING_M21, bhg5 = w1 & OVL_ING_M21, bhg3 = (w1 >> 21) & OVL_ING_M21;
+  const bool flipped = ((w0 >> 58) & 1ull) != 0;
+  const uint32_t evalue = (uint32_t)(w0 >> 42) & 0xFFFFu;
+  if (evalue > max_evalue) w0 &= ~OVL_ING_FLAGS;                       // both twins lose their flags
+  const uint64_t hi0 = w0 & ~((1ull << 42) - 1), hi1 = w1 & ~((1ull << 42) - 1);
+  *f0 = w0;
+  *r0 = hi0 | (flipped ? bhg3 : bhg5) | ((flipped ? bhg5 : bhg3) << 21);
+  *r1 = hi1 | (flipped ? ahg3 : ahg5) | ((flipped ? ahg5 : ahg3) << 21);
+  return (w0 & OVL_ING_FLAGS) != 0;
+}

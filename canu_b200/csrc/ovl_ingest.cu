@@ -18,8 +18,7 @@
 
 static inline unsigned div_up64(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
 
-#define ING_M21    ((1ull << 21) - 1)
-#define ING_FLAGS  (7ull << 59)                    // forOBT (59) | forDUP (60) | forUTG (61)
+#define ING_FLAGS  OVL_ING_FLAGS
 #define ING_DROP   0xFFFFFFFFFFFFFFFFull           // key of a record that no longer carries a flag (a_iid is never 2^32-1 ... and b)
 
 //  one thread per input record: both twins -> tmp[2i], tmp[2i+1] with their sort keys; out[0] += kept, out[1] |= bad IDs
@@ -34,18 +33,9 @@ k_ingest_mirror(const ovlb_record *__restrict__ in, uint64_t n, uint32_t max_eva
   if (i < n) {
     const ovlb_record f = in[i];
     if (f.a_iid == 0 || f.b_iid == 0 || f.a_iid > max_id || f.b_iid > max_id) atomicOr(&out[1], 1ull);
-    uint64_t w0 = f.dat0, w1 = f.dat1;
-    const uint64_t ahg5 = w0 & ING_M21, ahg3 = (w0 >> 21) & ING_M21, bhg5 = w1 & ING_M21, bhg3 = (w1 >> 21) & ING_M21;
-    const bool flipped = (w0 >> 58) & 1ull;
-    const uint32_t evalue = (uint32_t)(w0 >> 42) & 0xFFFFu;
-    if (evalue > max_evalue) w0 &= ~ING_FLAGS;                         // both twins lose their flags
-    const uint64_t hi0 = w0 & ~((1ull << 42) - 1), hi1 = w1 & ~((1ull << 42) - 1);
-    ovlb_record r;
+    ovlb_record ff = f, r;
     r.a_iid = f.b_iid; r.b_iid = f.a_iid;
-    r.dat0 = hi0 | (flipped ? bhg3 : bhg5) | ((flipped ? bhg5 : bhg3) << 21);
-    r.dat1 = hi1 | (flipped ? ahg3 : ahg5) | ((flipped ? ahg5 : ahg3) << 21);
-    ovlb_record ff = f; ff.dat0 = w0;
-    const bool keep = (w0 & ING_FLAGS) != 0;                           // the twin carries the same flags
+    const bool keep = ovl_ingest_twin(f.dat0, f.dat1, max_evalue, &ff.dat0, &r.dat0, &r.dat1) != 0;   // the twin carries the same flags
     tmp[2 * i] = ff; tmp[2 * i + 1] = r;
     idx[2 * i] = (uint32_t)(2 * i); idx[2 * i + 1] = (uint32_t)(2 * i + 1);
     kept = keep ? 2u : 0u;
