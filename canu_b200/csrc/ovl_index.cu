@@ -216,7 +216,7 @@ k_hash_tuples_compact(const uint64_t *__restrict__ fwd, const uint64_t *__restri
 #define BK_TARGET  4096                 // mean bucket size the bucket count is chosen for
 #define BK_TABLE   4096                 // hash-table entries per bucket
 #define BK_MAXDIST 3584                 // distinct k-mers a bucket may hold (load 0.875)
-#define BK_SMEM    (BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 8 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
+#define BK_SMEM    (BK_TABLE * 8 + BK_CAP * 4 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
 
 //  first tuple of every bucket (bucket = key >> shift) in the partitioned tuple array; offs[nb] = n
 __global__ void k_bucket_offsets(const uint64_t *__restrict__ key, uint64_t n, int shift, uint32_t nb, uint32_t *__restrict__ offs) {
@@ -235,17 +235,16 @@ k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ p
                int K, uint64_t mix_inv, uint32_t *__restrict__ occ, IndexSlot *__restrict__ tmp, uint32_t tmp_cap,
                uint32_t *__restrict__ gk, uint32_t *__restrict__ gv, unsigned long long *out) {
   extern __shared__ __align__(16) unsigned char bk_sm[];
-  uint64_t *tk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_CAP] mixed k-mer of each tuple; later: uint32 positions, grouped
-  uint32_t *tp = reinterpret_cast<uint32_t *>(tk + BK_CAP);              // [BK_CAP] position of each tuple
+  uint64_t *hk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_TABLE] mixed k-mer of the slot
+  uint32_t *gpos = reinterpret_cast<uint32_t *>(hk + BK_TABLE);          // [BK_CAP] positions grouped by (slot, class)
+  uint32_t *tp = gpos + BK_CAP;                                          // [BK_CAP] position of each tuple (keys stay in registers)
   uint16_t *ts = reinterpret_cast<uint16_t *>(tp + BK_CAP);              // [BK_CAP] slot << 3 | class
-  uint64_t *hk = reinterpret_cast<uint64_t *>(ts + BK_CAP);              // [BK_TABLE] mixed k-mer of the slot
-  uint32_t *hc = reinterpret_cast<uint32_t *>(hk + BK_TABLE);            // [BK_TABLE * 5] count -> start -> end of (slot, class)
+  uint32_t *hc = reinterpret_cast<uint32_t *>(ts + BK_CAP);              // [BK_TABLE * 5] count -> start -> end of (slot, class)
   uint32_t *hm = hc + BK_TABLE * 5;                                      // [BK_TABLE] first (smallest) position of the slot's k-mer
   __shared__ unsigned int n_dist, bad, slot_base;
   __shared__ unsigned int wsum[BK_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint64_t kmask = (1ull << (2 * K)) - 1;
-  uint32_t *gpos = reinterpret_cast<uint32_t *>(tk);
 
   for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
     const uint32_t s0 = offs[b], m = offs[b + 1] - s0;
