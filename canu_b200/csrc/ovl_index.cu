@@ -142,6 +142,40 @@ __device__ __forceinline__ bool warp_kmers(const uint64_t *__restrict__ w, int p
   return (p + K <= L) && (((uint32_t)iv & ((1u << K) - 1)) == 0);
 }
 
+//  The same for a warp that walks consecutive groups of one read (the probe kernel): the 2-bit codes of 32 consecutive
+//  dp4 words (512 bases) are converted once and kept one word per lane; a group needs five of them, so a window serves
+//  14 groups before it is reloaded -- one coalesced 256-byte load and one conversion per 14 groups instead of a
+//  40-byte load and a conversion per group.  `W` caches (read pointer, first word index, codes, invalid mask).
+struct KmerWindow { const uint64_t *w; int w0; uint32_t codes, inv; };
+
+__device__ __forceinline__ bool warp_kmers_win(KmerWindow &W, const uint64_t *__restrict__ w, int p0, int L, int K, int lane,
+                                               uint64_t &key, int &cls) {
+  const int need = (p0 >> 4) - 1;                       // first of the five words of this group (may be -1)
+  if (W.w != w || need < W.w0 || need + 4 > W.w0 + 31) {
+    W.w = w; W.w0 = need;
+    const int idx = need + lane;
+    W.codes = 0; W.inv = 0xFFFFu;
+    if (idx >= 0) W.codes = ovl_codes16(w[idx], &W.inv);
+  }
+  const int sb = need - W.w0;
+  const int j0 = sb + 1 + (lane >> 4);                 // first of my three words
+  const uint32_t cp = __shfl_sync(0xffffffffu, W.codes, j0 - 1), ip = __shfl_sync(0xffffffffu, W.inv, j0 - 1);
+  const uint32_t c0 = __shfl_sync(0xffffffffu, W.codes, j0),     i0 = __shfl_sync(0xffffffffu, W.inv, j0);
+  const uint32_t c1 = __shfl_sync(0xffffffffu, W.codes, j0 + 1), i1 = __shfl_sync(0xffffffffu, W.inv, j0 + 1);
+  const uint32_t c2 = __shfl_sync(0xffffffffu, W.codes, j0 + 2), i2 = __shfl_sync(0xffffffffu, W.inv, j0 + 2);
+  const int s = lane & 15;
+  const uint32_t lo = __funnelshift_r(c0, c1, 2 * s);
+  const uint32_t hi = __funnelshift_r(c1, c2, 2 * s);
+  key = (((uint64_t)hi << 32) | lo) & ((1ull << (2 * K)) - 1);
+  const uint64_t iv = ((uint64_t)i0 | ((uint64_t)i1 << 16) | ((uint64_t)i2 << 32)) >> s;
+  const int p = p0 + lane;
+  uint32_t pc, pi;
+  if (s > 0) { pc = (c0 >> (2 * (s - 1))) & 3u; pi = (i0 >> (s - 1)) & 1u; }
+  else       { pc = cp >> 30;                   pi = ip >> 15; }
+  cls = (p > 0 && pi == 0) ? (int)(1 + pc) : 0;
+  return (p + K <= L) && (((uint32_t)iv & ((1u << K) - 1)) == 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 //  K1: index build = tuple generation -> radix sort -> one slot per distinct k-mer
 //
@@ -631,6 +665,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
 
   const uint64_t total = 2 * n_groups;
   const uint64_t n_chunks = (total + PROBE_CHUNK - 1) / PROBE_CHUNK;
+  KmerWindow KW; KW.w = nullptr; KW.w0 = 0; KW.codes = 0; KW.inv = 0xFFFFu;
   for (uint64_t ch = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib; ch < n_chunks; ch += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
     const uint64_t gg_end = min(total, (ch + 1) * PROBE_CHUNK);
     uint32_t prev_r = 0xFFFFFFFFu; int prev_dir = -1; unsigned prev_top = 0;
@@ -646,7 +681,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       const bool carried = (r == prev_r && dir == prev_dir);    // the previous iteration was window group p0-32 of this read
 
       uint64_t key; int cls;
-      const bool ok = warp_kmers(w, p0, L, K, lane, key, cls);
+      const bool ok = warp_kmers_win(KW, w, p0, L, K, lane, key, cls);
       SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
       uint32_t my_idx = HT_NOTFOUND;
       {
