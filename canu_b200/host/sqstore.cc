@@ -1,4 +1,7 @@
 #include "sqstore.h"
+#include <unistd.h>
+#include <sys/mman.h>
+#include <fcntl.h>
 
 #include <cstring>
 #include <sys/stat.h>
@@ -7,7 +10,7 @@ namespace ovlhost {
 
 static bool file_exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
 
-SqStore::~SqStore() { for (FILE *f : blob_files_) if (f) fclose(f); }
+SqStore::~SqStore() { for (BlobMap &m : blob_maps_) if (m.p) munmap(const_cast<uint8_t *>(m.p), m.n); }
 
 bool SqStore::readFile(const std::string &name, std::vector<uint8_t> &out, std::string &err) const {
   std::string p = path_ + "/" + name;
@@ -76,7 +79,7 @@ bool SqStore::open(const std::string &path, std::string &err) {
   which_ = mr;
   if (file_exists(path_ + "/homopolymerCompression")) which_ |= SQ_COMPRESSED;
 
-  blob_files_.assign((size_t)num_blobs_ + 2, nullptr);
+  blob_maps_.assign((size_t)num_blobs_ + 2, BlobMap());
   return true;
 }
 
@@ -99,25 +102,32 @@ bool SqStore::fetchChunk(uint32_t id, const uint8_t *&chunk, uint32_t &chunk_len
   const uint64_t m1 = meta_[2 * (size_t)id + 1];
   const uint32_t segm = (uint32_t)((m1 >> 8) & 0xffff);
   const uint64_t byte = m1 >> 24;
-  if (segm >= blob_files_.size()) blob_files_.resize(segm + 1, nullptr);
-  if (!blob_files_[segm]) {
+  //  The blob files are mapped, not read: a read's chunk is handed out as a pointer into the mapping, so packing a
+  //  2-bit read is one memcpy (stdio cost 4.8 us per read: a seek, two freads and an intermediate copy).
+  if (segm >= blob_maps_.size()) blob_maps_.resize(segm + 1);
+  if (!blob_maps_[segm].p) {
     char name[64]; snprintf(name, sizeof(name), "/blobs.%04u", segm);
-    blob_files_[segm] = fopen((path_ + name).c_str(), "rb");
-    if (!blob_files_[segm]) { err = "cannot open '" + path_ + name + "'"; return false; }
-    setvbuf(blob_files_[segm], nullptr, _IOFBF, 1 << 20);
+    const std::string fn = path_ + name;
+    const int fd = ::open(fn.c_str(), O_RDONLY);
+    struct stat sb;
+    if (fd < 0 || fstat(fd, &sb) != 0) { if (fd >= 0) ::close(fd); err = "cannot open '" + fn + "'"; return false; }
+    void *m = sb.st_size ? mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : MAP_FAILED;
+    ::close(fd);
+    if (m == MAP_FAILED) { err = "cannot map '" + fn + "'"; return false; }
+    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    blob_maps_[segm].p = static_cast<const uint8_t *>(m); blob_maps_[segm].n = (size_t)sb.st_size;
   }
-  FILE *f = blob_files_[segm];
-  uint8_t hdr[8];
-  if (fseeko(f, (off_t)byte, SEEK_SET) != 0 || fread(hdr, 1, 8, f) != 8 || memcmp(hdr, "BLOB", 4) != 0) {
+  const BlobMap &M = blob_maps_[segm];
+  if (byte + 8 > M.n || memcmp(M.p + byte, "BLOB", 4) != 0) {
     err = "read " + std::to_string(id) + ": no BLOB at segment " + std::to_string(segm) + " byte " + std::to_string(byte);
     return false;
   }
-  uint32_t blen; memcpy(&blen, hdr + 4, 4);
-  blob_buf_.resize(blen);
-  if (fread(blob_buf_.data(), 1, blen, f) != blen) { err = "read " + std::to_string(id) + ": truncated BLOB"; return false; }
+  uint32_t blen; memcpy(&blen, M.p + byte + 4, 4);
+  if (byte + 8 + (uint64_t)blen > M.n) { err = "read " + std::to_string(id) + ": truncated BLOB"; return false; }
+  const uint8_t *blob = M.p + byte + 8;
   const char want = (which_ & SQ_RAW) ? 'R' : 'C';
   for (uint32_t p = 0; p + 8 <= blen; ) {
-    const uint8_t *t = &blob_buf_[p];
+    const uint8_t *t = blob + p;
     uint32_t clen; memcpy(&clen, t + 4, 4);
     if (t[1] == 'S' && t[2] == 'Q' && t[3] == (uint8_t)want && (t[0] == '2' || t[0] == '3' || t[0] == 'U')) {
       chunk = t + 8; chunk_len = clen; enc = (char)t[0];

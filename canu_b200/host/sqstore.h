@@ -64,8 +64,8 @@ class SqStore {
   uint32_t which_ = 0;
   std::vector<uint64_t> meta_;                            // 2 x uint64 per read (index 0 unused)
   std::vector<SqReadSeq> rawu_, rawc_, coru_, corc_;
-  std::vector<FILE *> blob_files_;
-  std::vector<uint8_t> blob_buf_;
+  struct BlobMap { const uint8_t *p = nullptr; size_t n = 0; };
+  std::vector<BlobMap> blob_maps_;                        // blobs.NNNN, memory-mapped read-only on first use
 };
 
 uint32_t homopolyCompress(const std::string &in, std::string &out);   // sequence-v1.C:203-261
