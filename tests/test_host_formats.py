@@ -69,3 +69,23 @@ def test_drop_in_cli_errors_like_the_reference(tmp_path):
     assert r.returncode == 1 and b"Unknown option 'b.seqStore'" in r.stderr
     r = subprocess.run([exe, "-k", "22", "-o", str(tmp_path / "x.ovb"), str(tmp_path / "nope.seqStore")], capture_output=True)
     assert r.returncode != 0
+
+
+def test_pack_ovb_roundtrip(tmp_path):
+    """ovltool pack-ovb: flat {u32 a, u32 b, u64 dat0, u64 dat1} records -> snappy .ovb + .oc, read back unchanged
+    (the path tools/ingest_timing.py uses to hand the same records to the reference's ovFile reader)."""
+    rng = np.random.default_rng(3)
+    n, n_reads = 100_003, 5000                      # more than two 43,680-record blocks, not a multiple of the block size
+    recs = np.zeros(n, dtype=[("a_iid", "<u4"), ("b_iid", "<u4"), ("w0", "<u8"), ("w1", "<u8")])
+    recs["a_iid"] = rng.integers(1, n_reads + 1, n); recs["b_iid"] = rng.integers(1, n_reads + 1, n)
+    recs["w0"] = rng.integers(0, 1 << 62, n, dtype=np.uint64); recs["w1"] = rng.integers(0, 1 << 63, n, dtype=np.uint64)
+    flat, ovb = str(tmp_path / "in.bin"), str(tmp_path / "out.ovb")
+    recs.tofile(flat)
+    subprocess.check_call([_tool(), "pack-ovb", flat, ovb, str(n_reads)])
+    lines = subprocess.check_output([_tool(), "dump-ovb", ovb]).decode().splitlines()
+    assert len(lines) == n
+    back = np.array([(int(x[0]), int(x[1]), int(x[2], 16), int(x[3], 16)) for x in (ln.split() for ln in lines)], dtype=recs.dtype)
+    assert np.array_equal(back, recs)
+    oc = gu.read_oc(str(tmp_path / "out.oc"))
+    want = np.bincount(recs["a_iid"], minlength=n_reads + 1) + np.bincount(recs["b_iid"], minlength=n_reads + 1)
+    assert oc[0] == n and np.array_equal(np.asarray(oc[1])[: n_reads + 1], want[: n_reads + 1])
