@@ -1194,6 +1194,9 @@ int ovl_build_index(ovlb_ctx *c) {
       const uint32_t nb = 1u << B;
       const int shift = 2 * K + 3 - B;
       const uint64_t tmp_cap = nt / 4 * 3 + (1u << 20);
+      //  the bucketed build sizes its slot scratch for the worst case (3/4 of the tuples distinct) before it knows the
+      //  real count; if that does not fit a third of the memory budget use the sorted build, which counts first
+      if (tmp_cap * (sizeof(IndexSlot) + 8) > c->mem_budget / 3) { bucketed = false; attempt--; continue; }
       EvTimer t2(c->stream);
       size_t tb = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)nt, shift, 2 * K + 3, c->stream);
