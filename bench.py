@@ -1,36 +1,44 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the ovl hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--genome BP --coverage X]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--chroms C --chrom-bp BP]
 
-Workload (config.workload): BASELINE.json configs[1] -- "5 Mbp bacterial 50x HiFi-like reads
-(ovlErrorRate 0.01)": uniform-random 5 Mbp genome, reads sampled from both strands with a log-normal
-length distribution (mean ~11 kb, HiFi-like), 0.1 % per-read error (sub:ins:del 4:3:3), k=22,
---minlength 500, --maxerate 0.01, one hash block x one ref block (-h 1-N -r 1-N).  Synthetic, seeded.
+Workload (config.workload): the read model of BASELINE.json configs[2] -- the one north_star quotes its target on
+("C. elegans-size 40x trimmed CLR-like reads, ovlErrorRate 0.06") -- as ONE overlap job sized so that a step fits the
+bench's time budget: a random genome of C chromosomes x BP bases (default 24 x 100 kbp = 2.4 Mbp; the full C3 is 100
+Mbp, the same job 42x longer: cost is linear in genome size at fixed coverage), 40x coverage, reads 10-20 kb from both
+strands, 3 % per-read error (sub:ins:del 4:3:3), read order shuffled; k=22, --minlength 500, --maxerate 0.06,
+`-h 1-N -r 1-N`.  Synthetic, seeded: every rank (and the reference arm) regenerates the same reads.
 
-One "step" = one pass of the hot path over the tile: k-mer index build over the hash reads, lookup +
-seed-run emission + chaining for every ref read in both orientations, banded extension of every
-candidate pair, overlap records packed on the device.
+One "step" = one pass of the hot path over the whole job: k-mer index build over the hash reads, lookup + seed-run
+emission + chaining for every ref read in both orientations, banded extension of every candidate pair, overlap records
+packed on the device, and the records of all ranks merged on rank 0.
 
-  value  read-pairs aligned per second (candidate oriented pairs entering Process_Matches =
-         "Kmer hits with olaps + Kmer hits without olaps" of the -s file), device pipeline only,
-         reads already resident in HBM (dp4-encoded) when the timed region starts.
-  e2e    the same metric through the C ABI with HOST buffers: packed reads copied host->device for
-         the hash and ref side, records copied device->host, inside the timed region (the ref batch's
-         upload is issued before ovlb_build_index and runs on the library's copy stream beside it).
-  roofline  the longest HBM-bound kernel launch of the step (by measured time per launch) against the measured
-         HBM peak; `stage_rooflines` lists every HBM-bound stage the same way.  The extension kernel is integer-ALU
-         bound (no GEMM shape, no tensor cores) and is reported under `extension` (HiFi tile of the step) and
-         `extension_noisy` (a small C3-like tile: 3 % read error, --maxerate 0.06, where it is >99 % of the time).
-  cpu_baseline  the UNMODIFIED reference overlapInCore (oracle/_ref, built by oracle/build_ref.sh) run
-         with -t <all host cores> on a bounded sample of the same workload (smaller genome, same
-         coverage / read model), rank 0 only.
+--gpus N (torchrun, one rank per GPU): STRONG scaling of that one job, the way north_star describes it.  The job has
+one hash block, so every GPU indexes it and the ref range is cut into N contiguous tiles of equal
+estimated work (`ovlb_plan_balanced`: only refID < hashID pairs are computed, so equal-base tiles are unequal work),
+assigned with `ovlb_assign_tiles`.  No collective on the data path; the only exchange is the gather of the 24-byte
+records on rank 0 (the reference's "merged on the host"), inside the timed region.
 
---impl reference times that reference binary instead (all host threads), same metric and unit.
-Under torchrun (N>1) every rank owns an independent tile of the same size (Canu's own job split:
-tiles share nothing), no collective on the data path; scaling is "weak".
+  value  read-pairs aligned per second (candidate oriented pairs entering Process_Matches = "Kmer hits with olaps +
+         Kmer hits without olaps" of the -s file) of the whole job, reads already resident in HBM (dp4-encoded) when
+         the timed region starts; device time (CUDA events), max over ranks.
+  e2e    the same through the C ABI with HOST buffers: every step copies the packed hash block and the rank's ref tile
+         host->device (pinned), and the merged records device->host on rank 0, inside the timed region.
+  parity rank 0 also runs the CPU-baseline sample (all reads of chromosome 0, a complete job of the same read model and
+         a strict subset of the reads the GPU arm times) on the GPU and compares the records with the reference
+         binary's: "identical" = same canonically sorted 24-byte records and same -s counters.
+  records_sha256  hash of the canonically sorted records of the whole job: equal at every N.
+  cpu_baseline / --impl reference: the UNMODIFIED reference overlapInCore (oracle/_ref, built by oracle/build_ref.sh),
+         -t <all host cores>, on that same sample.
+  hifi_tile (rank 0, N=1): the C2 tile of BASELINE.json configs[1] (5 Mbp x 50x HiFi-like, --maxerate 0.01), where the
+         index build and the lookup are a large share of the step: per-stage HBM rooflines; `roofline` is its longest
+         HBM-bound launch.  The job's own dominant kernel, k_extend_pairs, is integer-ALU / issue bound (no GEMM shape,
+         no tensor cores): reported under `extension` as DP Gcell/s with the warp-busy fraction of the launch.
 """
 import argparse
+import ctypes as C
+import hashlib
 import json
 import os
 import shutil
@@ -47,17 +55,31 @@ sys.path.insert(0, ROOT)
 
 K = 22
 MINLEN = 500
-ERATE = 0.01
-READ_ERR = 0.001
+ERATE = 0.06            # the job: C3 read model
+READ_ERR = 0.03
+COVERAGE = 40.0
+LEN_LO, LEN_HI = 10000, 20000
+HIFI_ERATE, HIFI_READ_ERR = 0.01, 0.001   # the secondary C2 tile
 REFBIN = os.path.join(ROOT, "oracle", "_ref", "bin")
+OURBIN = os.path.join(ROOT, "canu_b200", "bin")
 
 
-def make_workload(genome_bp, coverage, seed):
+def make_job(n_chroms, chrom_bp, seed=7001):
+    """(job reads in shuffled order, reads of chromosome 0 in generation order)."""
+    from canu_b200 import synth
+    per_chrom = []
+    for c in range(n_chroms):
+        g = synth.make_genome(chrom_bp, seed=seed + 10 * c)
+        per_chrom.append(synth.simulate_reads(g, COVERAGE, LEN_LO, LEN_HI, READ_ERR, seed=seed + 10 * c + 1))
+    allr = [r for rs in per_chrom for r in rs]
+    perm = np.random.default_rng(seed + 5).permutation(len(allr))
+    return [allr[i] for i in perm], per_chrom[0]
+
+
+def make_hifi_tile(genome_bp, coverage, seed):
     from canu_b200 import synth
     g = synth.make_genome(genome_bp, seed=seed)
-    # HiFi-like: log-normal lengths, mean ~11 kb, clipped to [3 kb, 30 kb]
-    reads = synth.simulate_reads(g, coverage, 3000, 30000, READ_ERR, seed=seed + 1, lognormal=(9.25, 0.3))
-    return reads
+    return synth.simulate_reads(g, coverage, 3000, 30000, HIFI_READ_ERR, seed=seed + 1, lognormal=(9.25, 0.3))
 
 
 class ClockSampler(threading.Thread):
@@ -106,21 +128,29 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def reference_run(reads, threads, workdir, tag, erate=None):
-    """Run the unmodified reference overlapper on `reads`; returns (seconds, pairs, overlaps)."""
-    erate = ERATE if erate is None else erate
+def pick_threads(n_reads, cores):
+    """A -t for which the reference does not drop the last ref read."""
+    for t in range(cores, 0, -1):
+        per = 1 + (n_reads - 1) // t // 8
+        if (n_reads - 1) % per != 0:
+            return t
+    return 1
+
+
+def reference_run(reads, cores, workdir, tag, erate, tech="-pacbio"):
+    """Run the unmodified reference overlapper on `reads` as one job; returns (seconds, pairs, stats dict, ovb path)."""
     from canu_b200 import synth
     fa = os.path.join(workdir, tag + ".fasta")
     st = os.path.join(workdir, tag + ".seqStore")
     if not os.path.exists(st):
         synth.write_fasta(fa, reads)
         subprocess.check_call([os.path.join(REFBIN, "sqStoreCreate"), "-o", st, "-minlength", "1000",
-                               "-pacbio-hifi", "lib", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                               tech, "lib", fa], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         os.remove(fa)
     n = len(reads)
     out = os.path.join(workdir, tag + ".ovb")
     stats = os.path.join(workdir, tag + ".stats")
-    cmd = [os.path.join(REFBIN, "overlapInCore"), "-t", str(threads), "-k", str(K), "--hashbits", "23",
+    cmd = [os.path.join(REFBIN, "overlapInCore"), "-t", str(pick_threads(n, cores)), "-k", str(K), "--hashbits", "23",
            "--hashload", "0.8", "--hashdatalen", str(10 ** 10), "--maxerate", str(erate), "--minlength", str(MINLEN),
            "-h", "1-%d" % n, "-r", "1-%d" % n, "-o", out, "-s", stats, st]
     t0 = time.perf_counter()
@@ -131,7 +161,29 @@ def reference_run(reads, threads, workdir, tag, erate=None):
         k, v = line.split("=")
         vals[k.strip()] = int(v)
     pairs = vals["Kmer hits without olaps"] + vals["Kmer hits with olaps"]
-    return dt, pairs, vals["Total overlaps produced"]
+    return dt, pairs, vals, out
+
+
+def read_ovb(path):
+    """Records of a reference-written .ovb as a structured array (through our ovltool's reader)."""
+    from canu_b200 import api
+    txt = subprocess.check_output([os.path.join(OURBIN, "ovltool"), "dump-ovb", path]).decode().split()
+    a = np.zeros(len(txt) // 4, dtype=api.RECORD_DTYPE)
+    a["a_iid"] = np.array(txt[0::4], dtype=np.uint64)
+    a["b_iid"] = np.array(txt[1::4], dtype=np.uint64)
+    a["w0"] = np.array([int(x, 16) for x in txt[2::4]], dtype=np.uint64)
+    a["w1"] = np.array([int(x, 16) for x in txt[3::4]], dtype=np.uint64)
+    return a
+
+
+def canon(recs):
+    return np.sort(recs, order=["a_iid", "b_iid", "w0", "w1"])
+
+
+def sample_text(args, n, bases, cores):
+    return ("all %d reads (%d bases) of chromosome 0 of the job's genome (%.0f kbp x %gx, same read model, a subset of "
+            "the reads the GPU arm times), run as one complete job -h 1-%d -r 1-%d, reference overlapInCore -t %d" % (
+                n, bases, args.chrom_bp / 1e3, COVERAGE, n, n, cores))
 
 
 def main():
@@ -140,11 +192,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome", type=int, default=5_000_000)
-    ap.add_argument("--coverage", type=float, default=50.0)
-    ap.add_argument("--sample-genome", type=int, default=1_200_000, help="genome size of the CPU-baseline sample")
-    ap.add_argument("--noisy-genome", type=int, default=500_000, help="genome size of the C3-like extension measurement (0 = skip)")
-    ap.add_argument("--noisy-sample-genome", type=int, default=60_000, help="genome size of its CPU-baseline sample")
+    ap.add_argument("--chroms", type=int, default=24, help="chromosomes of the job's genome")
+    ap.add_argument("--chrom-bp", type=int, default=100_000, help="bases per chromosome (chromosome 0 is the CPU sample)")
+    ap.add_argument("--ref-runs", type=int, default=2, help="cap on the timed reference runs (each is the same deterministic sample)")
+    ap.add_argument("--hifi-genome", type=int, default=5_000_000, help="genome of the secondary C2 tile (0 = skip)")
+    ap.add_argument("--hifi-coverage", type=float, default=50.0)
+    ap.add_argument("--hifi-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the steps of the end-to-end (host buffers) timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -152,35 +206,40 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    workload = "C2: %.1f Mbp random genome, %gx HiFi-like reads (log-normal ~11 kb, %.1f%% read error), k=%d, --maxerate %g, --minlength %d, single hash x ref tile" % (
-        args.genome / 1e6, args.coverage, READ_ERR * 100, K, ERATE, MINLEN)
+    workload = ("C3 read model as one job: %d x %.0f kbp random genome (%.2f Mbp), %gx, %d-%d kb reads, %.0f%% read error, "
+                "shuffled; k=%d, --maxerate %g, --minlength %d, -h 1-N -r 1-N; one hash block, ref range cut into n_gpus "
+                "cost-balanced tiles" % (args.chroms, args.chrom_bp / 1e3, args.chroms * args.chrom_bp / 1e6, COVERAGE,
+                                         LEN_LO // 1000, LEN_HI // 1000, READ_ERR * 100, K, ERATE, MINLEN))
+    config = {"workload": workload, "l2": "inputs (dp4 reads + index) exceed the 126 MB L2"}
+    have_ref = os.path.exists(os.path.join(REFBIN, "overlapInCore"))
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        if not os.path.exists(os.path.join(REFBIN, "overlapInCore")):
+        if not have_ref:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/overlapInCore was not built (run oracle/build_ref.sh where /root/reference exists)"}))
             return 0
         wd = tempfile.mkdtemp(prefix="ovlbench_ref_")
         try:
-            reads = make_workload(args.sample_genome, args.coverage, seed=1001)
-            for _ in range(max(args.warmup, 0) and 1):          # one warm-up run is enough to warm the page cache
-                reference_run(reads, cores, wd, "s")
+            _, sample = make_job(1, args.chrom_bp)
+            if args.warmup > 0:
+                reference_run(sample, cores, wd, "s", ERATE)            # one warm-up run: page cache, store built
             ts, pairs = [], 0
-            for _ in range(args.steps):
-                dt, pairs, _ = reference_run(reads, cores, wd, "s")
+            runs = max(1, min(args.steps, args.ref_runs))
+            for _ in range(runs):
+                dt, pairs, _, _ = reference_run(sample, cores, wd, "s", ERATE)
                 ts.append(dt)
             t = float(np.mean(ts))
             v = pairs / t
-            sample = "%.2f Mbp genome x %gx (%d reads, %d bases), whole tile per step, reference overlapInCore -t %d" % (
-                args.sample_genome / 1e6, args.coverage, len(reads), sum(r.size for r in reads), cores)
+            stxt = sample_text(args, len(sample), int(sum(r.size for r in sample)), cores) + (
+                "; %d timed runs of %.1f s (capped: the run is deterministic), %d pairs per run" % (runs, t, pairs))
             print(json.dumps({
                 "impl": "reference", "metric": "ovl read-pairs aligned/sec", "value": v, "unit": "read-pairs/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": workload, "sample": sample},
-                "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "read-pairs/s", "cores": cores, "kind": "reference", "sample": stxt},
                 "e2e": {"value": v, "unit": "read-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             }))
         finally:
@@ -195,17 +254,31 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=dev)
 
-    reads = make_workload(args.genome, args.coverage, seed=2001 + 17 * rank)
+    reads, sample = make_job(args.chroms, args.chrom_bp)
     n_reads = len(reads)
-    total_bases = int(sum(r.size for r in reads))
-    prm = api.OverlapParams(kmer_len=K, max_erate=ERATE, min_olap_len=MINLEN, max_read_len=max(r.size for r in reads))
+    lens = [int(r.size) for r in reads]
+    total_bases = int(sum(lens))
+    max_len = max(lens)
+
+    # the job's tile grid: one hash block (everything fits HBM), ref range cut into `world` cost-balanced tiles
+    tiles = api.plan_balanced(lens, MINLEN, world)
+    owner = api.assign_tiles(tiles, world)
+    mine = [t for t, o in zip(tiles, owner) if o == rank]
+    assert len(mine) <= 1, "one launch per GPU and hash block"
+    prm = api.OverlapParams(kmer_len=K, max_erate=ERATE, min_olap_len=MINLEN, max_read_len=max_len)
     ov = api.Overlapper(prm, device=local_rank)
-    packed = api.PackedReads(reads, first_read_id=1, min_len=MINLEN)
+    hpacked = api.PackedReads(reads, first_read_id=1, min_len=MINLEN)
+    if mine:
+        rb, re_ = mine[0]["ref_bgn"], mine[0]["ref_end"]
+    else:
+        rb, re_ = 1, 0
+    rpacked = api.PackedReads(reads[rb - 1:re_], first_read_id=rb, min_len=MINLEN)
     del reads
 
     def barrier():
@@ -214,14 +287,54 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident steps: index build + seeding + extension (reads already in HBM)
-    ov.load_hash_reads(packed)
+    rec_cap = [1 << 16]
+    rec_dev = [torch.empty(rec_cap[0] * 24, dtype=torch.uint8, device=dev)]
+    merged = {}
+
+    def fetch_to_device(n):
+        if n > rec_cap[0]:
+            rec_cap[0] = int(n * 1.25) + 1024
+            rec_dev[0] = torch.empty(rec_cap[0] * 24, dtype=torch.uint8, device=dev)
+        k = C.c_uint64()
+        api._check(ov.L.ovlb_fetch_records(ov._h, rec_dev[0].data_ptr(), rec_cap[0], C.byref(k)))
+        return k.value
+
+    def merge_on_rank0(n):
+        """Gather the ranks' records on rank 0 (device memory); returns (tensor of 24-byte rows, count) on rank 0."""
+        if dist is None:
+            return rec_dev[0], n
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        cl = [int(c.item()) for c in cnts]
+        mx = max(max(cl), 1)
+        if mx > rec_cap[0]:
+            old = rec_dev[0]
+            rec_cap[0] = int(mx * 1.25) + 1024
+            rec_dev[0] = torch.empty(rec_cap[0] * 24, dtype=torch.uint8, device=dev)
+            rec_dev[0][: n * 24] = old[: n * 24]
+        send = rec_dev[0][: mx * 24]
+        if rank == 0:
+            key = ("g", mx)
+            if key not in merged:
+                merged.clear()
+                merged[key] = [torch.empty(mx * 24, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.gather(send, merged[key], dst=0)
+            out = torch.cat([merged[key][r][: cl[r] * 24] for r in range(world)])
+            return out, sum(cl)
+        dist.gather(send, None, dst=0)
+        return None, 0
+
+    # ---- device-resident steps: index build + seeding + extension + merge (reads already in HBM)
+    ov.load_hash_reads(hpacked)
     ov.build_index()
-    ov.stage_ref_batch(packed)
+    ov.stage_ref_batch(rpacked)
 
     def step():
         ov.build_index()
-        return ov.run_staged()
+        n = ov.run_staged() if mine else 0
+        n = fetch_to_device(n) if n else 0
+        return merge_on_rank0(n)
 
     for _ in range(args.warmup):
         step()
@@ -231,178 +344,221 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    # CUDA events on the library's own stream (the one every kernel is launched on): ovlb_timer_start/stop
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    ov.timer_start()
-    n_rec = 0
+    ev0.record()
+    lib_ms = 0.0
     for _ in range(args.steps):
-        n_rec = step()
+        out_t, out_n = step()
         t = ov.timings()
+        lib_ms += t["index_tuples_ms"] + t["index_sort_ms"] + t["index_table_ms"] + t["index_skip_ms"] + (t["total_ms"] if mine else 0.0)
         for k2, v2 in t.items():
             stage_ms[k2] = stage_ms.get(k2, 0.0) + v2 / args.steps
-    dev_ms = ov.timer_stop()
+    ev1.record()
     barrier()
     wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)          # device clock around the K steps (library stream work is synchronous inside it)
     clocks = sampler.stop()
     launches = ov.kernel_launches() - launches0
     ctr = ov.counters()
-    wall_ms = wall * 1e3
     pairs_step = ctr["pairs"] / args.steps
     cells_step = ctr["dp_cells"] / args.steps
 
-    # ---- end to end through the C ABI with HOST buffers: packed reads are copied host->device for the hash side and
-    #      again for the ref side, overlap records device->host, every step; host buffers are page-locked
-    packed.pin()
-    rec_host = np.zeros(max(n_rec, 1) + 1024, dtype=api.RECORD_DTYPE)
-    api._check(api.load_library().ovlb_host_register(rec_host.ctypes.data, rec_host.nbytes))
+    job_hash, n_job_recs = None, 0
+    if rank == 0:
+        recs = np.frombuffer(out_t[: out_n * 24].cpu().numpy().tobytes(), dtype=api.RECORD_DTYPE)
+        n_job_recs = int(recs.size)
+        job_hash = hashlib.sha256(canon(recs).tobytes()).hexdigest()[:16]
+
+    # ---- end to end through the C ABI with HOST buffers
+    hpacked.pin()
+    rpacked.pin()
+    host_out = {"buf": None}
 
     def e2e_step():
-        ov.load_hash_reads(packed)                 # H2D of the hash block + encode (compute stream)
-        ov.stage_ref_batch(packed)                 # H2D of the ref batch + encode on the copy stream: overlaps the index build
+        ov.load_hash_reads(hpacked)                # H2D of the hash block + encode
+        if mine:
+            ov.stage_ref_batch(rpacked)            # H2D of the ref tile on the copy stream: overlaps the index build
         ov.build_index()
-        ov.run_staged()                            # waits for the ref upload, then seeding + extension
-        k = ov.fetch_records_into(rec_host)        # D2H of the records
-        return rec_host[:k]
+        n = ov.run_staged() if mine else 0
+        n = fetch_to_device(n) if n else 0
+        t_, n_ = merge_on_rank0(n)
+        if rank == 0:
+            if host_out["buf"] is None or host_out["buf"].numel() < n_ * 24:
+                host_out["buf"] = torch.empty(int(n_ * 24 * 1.25) + 1024, dtype=torch.uint8, pin_memory=True)
+            host_out["buf"][: n_ * 24].copy_(t_[: n_ * 24], non_blocking=True)     # D2H of the merged records
+            torch.cuda.synchronize()
+        return n_
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    ov.timer_start()
-    for _ in range(args.steps):
-        recs = e2e_step()
-    e2e_dev_ms = ov.timer_stop()
+    ev0.record()
+    n_e2e = 0
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(e2e_steps):
+        n_e2e = e2e_step()
+    ev1.record()
     barrier()
-    e2e_wall = max(time.perf_counter() - t0, e2e_dev_ms * 1e-3)   # host packing/copies count too: take the larger
-    h2d = 2 * (packed.packed_bytes + n_reads * (8 + 4 + 8 + 8))
-    d2h = int(recs.nbytes)
+    e2e_ms = max((time.perf_counter() - t0) * 1e3, ev0.elapsed_time(ev1)) * args.steps / e2e_steps     # host packing/copies count too: take the larger; scaled to K steps
+    h2d = hpacked.packed_bytes + hpacked.n_reads * 28 + (rpacked.packed_bytes + rpacked.n_reads * 28 if mine else 0)
+    d2h = n_e2e * 24 if rank == 0 else 0
 
-    # ---- secondary: the extension kernel where it dominates (C3-like reads: 3 % error, --maxerate 0.06), rank 0, N=1 only
-    noisy = None
-    if rank == 0 and world == 1 and args.noisy_genome > 0:
-        from canu_b200 import synth
-
-        def noisy_tile(genome_bp, seed):
-            g = synth.make_genome(genome_bp, seed=seed)
-            rd = synth.simulate_reads(g, 40, 10000, 20000, 0.03, seed=seed + 1)
-            prm_n = api.OverlapParams(kmer_len=K, max_erate=0.06, min_olap_len=MINLEN, max_read_len=max(r.size for r in rd))
-            ovn = api.Overlapper(prm_n, device=local_rank)
-            pk = api.PackedReads(rd, first_read_id=1, min_len=MINLEN)
-            ovn.load_hash_reads(pk); ovn.build_index(); ovn.stage_ref_batch(pk)
-            ovn.run_staged()                                   # warm-up
-            ovn.reset_counters()
-            torch.cuda.synchronize()
-            ovn.timer_start()
-            ovn.build_index(); ovn.run_staged()
-            ms = ovn.timer_stop()
-            t = ovn.timings(); cn = ovn.counters()
-            ovn.close()
-            return rd, ms, t, cn
-
-        rd, ms, t, cn = noisy_tile(args.noisy_genome, 3001)
-        noisy = {"workload": "C3-like tile: %.2f Mbp x 40x, 10-20 kb reads, 3%% read error, --maxerate 0.06" % (args.noisy_genome / 1e6),
-                 "ms_per_step": ms, "read_pairs_per_s": cn["pairs"] / (ms * 1e-3), "extend_ms": t["extend_ms"],
-                 "kernel_gcells_per_s": cn["dp_cells"] / 1e9 / (t["extend_ms"] * 1e-3), "cells_per_step": cn["dp_cells"],
-                 "extend_calls": cn["extend_calls"], "pairs_per_step": cn["pairs"]}
-        if not args.no_cpu_baseline and os.path.exists(os.path.join(REFBIN, "overlapInCore")) and args.noisy_sample_genome > 0:
-            # same read model, smaller genome; the DP cell count of the sample comes from our counters (cell counts are
-            # part of the parity tests), the time from the reference binary on all host cores
-            srd, sms, st, scn = noisy_tile(args.noisy_sample_genome, 3101)
-            wd = tempfile.mkdtemp(prefix="ovlbench_cpun_")
-            try:
-                dt, sp, _ = reference_run(srd, cores, wd, "n", erate=0.06)
-                noisy["cpu_baseline"] = {"gcells_per_s": scn["dp_cells"] / 1e9 / dt, "read_pairs_per_s": sp / dt, "cores": cores,
-                                         "kind": "reference", "seconds": dt,
-                                         "sample": "%.3f Mbp x 40x (%d reads), whole tile, reference overlapInCore -t %d; same sample on the GPU: %.1f ms" % (
-                                             args.noisy_sample_genome / 1e6, len(srd), cores, sms)}
-                assert sp == scn["pairs"], ("candidate-pair count differs from the reference", sp, scn["pairs"])
-            finally:
-                shutil.rmtree(wd, ignore_errors=True)
-
-    tt = torch.tensor([dev_ms / args.steps, e2e_wall * 1e3 / args.steps, pairs_step, cells_step, h2d, d2h], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dev_ms / args.steps, e2e_ms / args.steps, pairs_step, cells_step, h2d, d2h, launches,
+                       ctr["ext_busy_ns"], ctr["ext_capacity_ns"], stage_ms.get("extend_ms", 0.0), lib_ms / args.steps],
+                      dtype=torch.float64, device=dev)
     if dist is not None:
-        tmax = tt.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = tt.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_step, e2e_ms = tmax[0].item(), tmax[1].item()
-        pairs_all, cells_all = tsum[2].item(), tsum[3].item()
-        h2d, d2h = int(tsum[4].item()), int(tsum[5].item())        # whole job, like `value`
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        per_rank = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(per_rank, tt)
     else:
-        ms_step, e2e_ms, pairs_all, cells_all = tt[0].item(), tt[1].item(), pairs_step, cells_step
+        tmax, tsum, per_rank = tt, tt, [tt]
+    ms_step, e2e_step_ms = tmax[0].item(), tmax[1].item()
+    pairs_all, cells_all = tsum[2].item(), tsum[3].item()
 
-    if rank == 0:
-        peaks, which = measured_peaks()
+    if rank != 0:
+        ov.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peaks, which = measured_peaks()
+    line = {
+        "metric": "ovl read-pairs aligned/sec", "value": pairs_all / (ms_step * 1e-3), "unit": "read-pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": config,
+        "e2e": {"value": pairs_all / (e2e_step_ms * 1e-3), "unit": "read-pairs/s",
+                "h2d_bytes_per_step": int(tsum[4].item()), "d2h_bytes_per_step": int(tsum[5].item()),
+                "timed_steps": max(1, min(args.steps, args.e2e_steps))},
+        "gpu_launches": int(tsum[6].item()),
+        "clocks": clocks,
+        "job": {"reads": n_reads, "bases": total_bases, "pairs_per_step": pairs_all, "overlaps_per_step": n_job_recs,
+                "dp_cells_per_step": cells_all, "records_sha256": job_hash,
+                "tiles": [{k2: t[k2] for k2 in ("hash_bgn", "hash_end", "ref_bgn", "ref_end", "ref_bases")} | {"owner": o, "cost": round(t["cost"])}
+                          for t, o in zip(tiles, owner)],
+                "per_rank_ms": [round(p[0].item(), 2) for p in per_rank],
+                "per_rank_extend_ms": [round(p[9].item(), 2) for p in per_rank],
+                "per_rank_library_ms": [round(p[10].item(), 2) for p in per_rank],
+                "host_wall_ms_per_step": wall * 1e3 / args.steps},
+        "extension": {"kernel": "k_extend_pairs", "bound": "int32 ALU / issue (integer DP: no tensor cores, 0.25 B/cell to HBM)",
+                      "gcells_per_s": cells_all / 1e9 / (ms_step * 1e-3),
+                      "kernel_gcells_per_s_per_gpu": [round(p[3].item() / 1e9 / (p[9].item() * 1e-3), 2) if p[9].item() > 0 else None for p in per_rank],
+                      "warp_busy_frac": round(tsum[7].item() / tsum[8].item(), 4) if tsum[8].item() > 0 else None,
+                      "note": "warp_busy_frac = time the persistent warps spent between their first and last pair / (launched warps x launch duration): 1 - tail loss"},
+        "stages_ms": {k2: round(v2, 3) for k2, v2 in stage_ms.items()},
+    }
+    ov.close()
+
+    # ---- parity + CPU baseline: the sample (chromosome 0's reads) through the GPU path and through the reference binary
+    wd = tempfile.mkdtemp(prefix="ovlbench_cpu_")
+    try:
+        if world > 1:
+            raise StopIteration
+        sm = max(r.size for r in sample)
+        sprm = api.OverlapParams(kmer_len=K, max_erate=ERATE, min_olap_len=MINLEN, max_read_len=sm)
+        srecs, sctr = api.overlap_in_core(sample, sprm, device=local_rank)
+        stxt = sample_text(args, len(sample), int(sum(r.size for r in sample)), cores)
+        if have_ref and not args.no_cpu_baseline:
+            dt, sp, svals, ovb = reference_run(sample, cores, wd, "s", ERATE)
+            want = canon(read_ovb(ovb))
+            got = canon(srecs)
+            same_recs = want.size == got.size and want.tobytes() == got.tobytes()
+            same_stats = (svals["Kmer hits without olaps"] == sctr["kmer_hits_without_olap"] and
+                          svals["Kmer hits with olaps"] == sctr["kmer_hits_with_olap"] and
+                          svals["Multiple overlaps/pair"] == sctr["multi_overlap"] and
+                          svals["Contained overlaps"] == sctr["contained"] and svals["Dovetail overlaps"] == sctr["dovetail"] and
+                          svals["Total overlaps produced"] == sctr["total_overlaps"])
+            line["parity"] = "identical" if (same_recs and same_stats) else "DIFFERENT"
+            line["parity_detail"] = {"sample_records": int(got.size), "reference_records": int(want.size), "records_identical": bool(same_recs),
+                                     "stats_identical": bool(same_stats), "sample_pairs": sp,
+                                     "sha256_gpu": hashlib.sha256(got.tobytes()).hexdigest()[:16],
+                                     "sha256_reference": hashlib.sha256(want.tobytes()).hexdigest()[:16]}
+            line["cpu_baseline"] = {"value": sp / dt, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
+                                    "sample": stxt + "; %.1f s, %d pairs" % (dt, sp),
+                                    "gcells_per_s": sctr["dp_cells"] / 1e9 / dt}
+        else:
+            line["parity"] = "unchecked (reference binary not built)" if not have_ref else "unchecked (--no-cpu-baseline)"
+            line["cpu_baseline"] = None
+    except StopIteration:
+        line["parity"] = "records_sha256 equals the N=1 line's (the sample check against the reference binary runs at N=1)"
+        line["cpu_baseline"] = None
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+    # ---- secondary: the C2 tile (HiFi-like reads), where index build and lookup matter: per-stage HBM rooflines
+    roofline = None
+    if world == 1 and args.hifi_genome > 0:
+        hreads = make_hifi_tile(args.hifi_genome, args.hifi_coverage, seed=2001)
+        hprm = api.OverlapParams(kmer_len=K, max_erate=HIFI_ERATE, min_olap_len=MINLEN, max_read_len=max(r.size for r in hreads))
+        hov = api.Overlapper(hprm, device=local_rank)
+        hp = api.PackedReads(hreads, first_read_id=1, min_len=MINLEN)
+        hbases = int(sum(r.size for r in hreads))
+        del hreads
+        hov.load_hash_reads(hp); hov.build_index(); hov.stage_ref_batch(hp)
+        for _ in range(3):
+            hov.build_index(); hov.run_staged()
+        hov.reset_counters()
+        hst = {}
+        torch.cuda.synchronize()
+        hov.timer_start()
+        for _ in range(args.hifi_steps):
+            hov.build_index(); hn = hov.run_staged()
+            t = hov.timings()
+            for k2, v2 in t.items():
+                hst[k2] = hst.get(k2, 0.0) + v2 / args.hifi_steps
+        hms = hov.timer_stop() / args.hifi_steps
+        hc = hov.counters()
+        hov.close()
+        hk, rk, sr = (hc[x] / args.hifi_steps for x in ("hash_kmers", "ref_kmers", "seed_runs"))
+        hpairs = hc["pairs"] / args.hifi_steps
         # Rooflines of the HBM-bound stages (DESIGN.md section 4 states the per-unit bytes).  Stage times are CUDA-event
         # brackets on the library's stream around each kernel (group) of the step; a stage of n identical launches
-        # (the radix-sort passes) is divided by n: `achieved` is algorithmic bytes PER LAUNCH over time PER LAUNCH.
-        hk, rk, sh, sr = (ctr[x] / args.steps for x in ("hash_kmers", "ref_kmers", "seed_hits", "seed_runs"))
-        bbits = 8                                                   # bucket bits of the bucketed index build (ovl_build_index)
-        while bbits < 2 * K and (int(hk) >> bbits) > 4096:
-            bbits += 1
-        sort_passes = (bbits + 7) // 8
+        # is divided by n: `achieved` is algorithmic bytes PER LAUNCH over time PER LAUNCH.
         stage_def = {   # stage: (kernel, launches, algorithmic bytes per launch)
-            "index_tuples_ms": ("k_hash_tuples_compact", 1, hk * (0.5 + 12)),             # dp4 base read + (key, position) tuple write
-            "index_sort_ms": ("cub::DeviceRadixSortOnesweep (one 8-bit pass over the bucket bits)", sort_passes, hk * 12 * 2),   # every pass reads and writes every 12 B tuple
-            "index_table_ms": ("k_bucket_group + path sort + k_path_slots", 1, hk * (12 + 4)),    # partitioned tuples read once, grouped positions written (+ 3 x 32 B per distinct k-mer, not counted)
-            "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),                      # dp4 base + one 32 B slot per window
-            "expand_ms": ("k_expand_small + k_expand_large", 1, sr * (4 + 16 + 16)),   # occurrence + bases compared + run record written
-            "sort_ms": ("cub::DeviceRadixSortOnesweep (runs)", 8, sr * 16 * 2),
+            "index_tuples_ms": ("k_hash_tuples_compact", 1, hk * (0.5 + 12)),
+            "index_sort_ms": ("radix partition over the bucket bits (per pass)", 2, hk * 12 * 2),
+            "index_table_ms": ("k_bucket_group + path sort + k_path_slots", 1, hk * (12 + 4)),
+            "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),
+            "expand_ms": ("k_expand_small + k_expand_large", 1, sr * (4 + 16 + 16)),
+            "sort_ms": ("radix sort of the seed runs", 8, sr * 16 * 2),
             "chain_ms": ("k_pair_scatter + k_chain_pairs", 1, sr * (16 + 12 + 12 + 16)),
         }
         stage_roof = {}
         for st_name, (kname, nl, ab) in stage_def.items():
-            ms_l = stage_ms.get(st_name, 0.0) / nl
+            ms_l = hst.get(st_name, 0.0) / nl
             if ms_l <= 0:
                 continue
             ach = ab / (ms_l * 1e-3) / 1e9
             stage_roof[st_name.replace("_ms", "")] = {"kernel": kname, "launches": nl, "ms_per_launch": round(ms_l, 4),
                                                       "achieved": round(ach, 1), "frac": round(ach / peaks["hbm_gbs"], 4)}
-        dom = max(stage_roof, key=lambda k2: stage_roof[k2]["ms_per_launch"])          # longest single HBM-bound launch
-        dom_all = max(("index_tuples_ms", "index_sort_ms", "index_table_ms", "probe_ms", "expand_ms", "sort_ms", "chain_ms", "extend_ms"),
-                      key=lambda k2: stage_ms.get(k2, 0.0))
-        # DRAM traffic of that kernel per launch from the committed ncu --set full capture of this same workload
+        dom = max(stage_roof, key=lambda k2: stage_roof[k2]["ms_per_launch"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath) and args.genome == 5_000_000 and args.coverage == 50.0:
-            traffic = json.load(open(tpath)).get(dom)
+        if os.path.exists(tpath) and args.hifi_genome == 5_000_000 and args.hifi_coverage == 50.0:
+            traffic = json.load(open(tpath)).get(dom + "_ms")
+        index_ms = hst.get("index_tuples_ms", 0) + hst.get("index_sort_ms", 0) + hst.get("index_table_ms", 0)
         roofline = {"bound": "hbm", "kernel": stage_roof[dom]["kernel"], "stage": dom, "achieved": stage_roof[dom]["achieved"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic, "peak_source": which,
-                    "ms_per_launch": stage_roof[dom]["ms_per_launch"], "longest_stage_of_step": dom_all.replace("_ms", ""),
-                    "note": "longest HBM-bound kernel launch of the step; the extension kernel (longest stage) is integer-ALU bound and is reported under 'extension' / 'extension_noisy'"}
-        line = {
-            "metric": "ovl read-pairs aligned/sec", "value": pairs_all / (ms_step * 1e-3), "unit": "read-pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload, "reads_per_gpu": n_reads, "bases_per_gpu": total_bases,
-                       "l2": "inputs (%.0f MB dp4 + index) exceed the 126 MB L2" % (total_bases * 1.0 / 1e6)},
-            "e2e": {"value": pairs_all / (e2e_ms * 1e-3), "unit": "read-pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roofline,
+                    "ms_per_launch": stage_roof[dom]["ms_per_launch"], "measured_on": "hifi_tile",
+                    "note": "longest HBM-bound kernel launch of the C2 tile; the job's dominant kernel (k_extend_pairs) is integer-ALU bound, see 'extension'"}
+        line["hifi_tile"] = {
+            "workload": "C2: %.1f Mbp x %gx HiFi-like reads (log-normal ~11 kb, %.1f%% read error), --maxerate %g, single hash x ref tile, inputs resident" % (
+                args.hifi_genome / 1e6, args.hifi_coverage, HIFI_READ_ERR * 100, HIFI_ERATE),
+            "bases": hbases, "ms_per_step": hms, "read_pairs_per_s": hpairs / (hms * 1e-3), "pairs_per_step": hpairs, "overlaps_per_step": int(hn),
+            "stages_ms": {k2: round(v2, 3) for k2, v2 in hst.items()},
             "stage_rooflines": stage_roof,
-            "extension": {"gcells_per_s": cells_all / 1e9 / (ms_step * 1e-3),
-                          "kernel_gcells_per_s": cells_step / 1e9 / (stage_ms["extend_ms"] * 1e-3) if stage_ms.get("extend_ms") else None,
-                          "cells_per_step": cells_all},
-            "extension_noisy": noisy,
-            "stages_ms": {k2: round(v2, 3) for k2, v2 in stage_ms.items()},
-            "overlaps_per_step": int(n_rec), "pairs_per_step": pairs_all, "host_wall_ms_per_step": wall_ms / args.steps,
+            "index_build": {"ms": round(index_ms, 3), "survey_8d_bytes_per_kmer": 17.25,
+                            "achieved_gbs": round(hk * 17.25 / (index_ms * 1e-3) / 1e9, 1) if index_ms > 0 else None,
+                            "frac": round(hk * 17.25 / (index_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4) if index_ms > 0 else None},
+            "extension_kernel_gcells_per_s": hc["dp_cells"] / args.hifi_steps / 1e9 / (hst["extend_ms"] * 1e-3) if hst.get("extend_ms") else None,
         }
-        if not args.no_cpu_baseline and os.path.exists(os.path.join(REFBIN, "overlapInCore")):
-            wd = tempfile.mkdtemp(prefix="ovlbench_cpu_")
-            try:
-                sreads = make_workload(args.sample_genome, args.coverage, seed=1001)
-                reference_run(sreads, cores, wd, "s")
-                dt, sp, _ = reference_run(sreads, cores, wd, "s")
-                line["cpu_baseline"] = {"value": sp / dt, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
-                                        "sample": "%.2f Mbp genome x %gx (%d reads), whole tile, reference overlapInCore -t %d, %.1f s" % (
-                                            args.sample_genome / 1e6, args.coverage, len(sreads), cores, dt)}
-            finally:
-                shutil.rmtree(wd, ignore_errors=True)
-        else:
-            line["cpu_baseline"] = None
-        print(json.dumps(line))
-    ov.close()
+    line["roofline"] = roofline
+    print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

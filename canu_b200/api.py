@@ -52,7 +52,7 @@ class _Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "kmer_hits_without_olap", "kmer_hits_with_olap", "kmer_hits_skipped", "multi_overlap",
         "total_overlaps", "contained", "dovetail", "extend_calls", "dp_cells", "hash_kmers",
-        "ref_kmers", "seed_hits", "seed_runs", "pairs")]
+        "ref_kmers", "seed_hits", "seed_runs", "pairs", "ext_busy_ns", "ext_capacity_ns")]
 
 
 class _Tile(C.Structure):
@@ -78,7 +78,7 @@ EXPORTS = [
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
-    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_assign_tiles",
+    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_assign_tiles",
 ]
 
 
@@ -130,6 +130,8 @@ def load_library():
     L.ovlb_plan_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                   C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_assign_tiles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.ovlb_plan_balanced.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     _LIB = L
     return L
 
@@ -379,6 +381,20 @@ def plan_tiles(read_lens, min_olap_len, hash_block_len, ref_block_len, hash_rang
     arr = (_Tile * max(cnt.value, 1))()
     _check(L.ovlb_plan_tiles(rl.ctypes.data, n, min_olap_len, hash_block_len, ref_block_len, hb, he, rb, re_,
                              int(strict_reference), C.cast(arr, C.c_void_p), cnt.value, C.byref(cnt)))
+    return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
+
+
+def plan_balanced(read_lens, min_olap_len, n_parts, hash_range=None, ref_range=None):
+    """Cut one hash block's ref range into n_parts contiguous tiles of equal estimated work (ovlb_plan_balanced)."""
+    L = load_library()
+    n = len(read_lens)
+    rl = np.zeros(n + 2, dtype=np.uint32)
+    rl[1:n + 1] = np.asarray(read_lens, dtype=np.uint32)
+    hb, he = hash_range if hash_range else (1, n)
+    rb, re_ = ref_range if ref_range else (1, n)
+    cnt = C.c_uint64()
+    arr = (_Tile * max(n_parts, 1))()
+    _check(L.ovlb_plan_balanced(rl.ctypes.data, n, min_olap_len, hb, he, rb, re_, n_parts, C.cast(arr, C.c_void_p), n_parts, C.byref(cnt)))
     return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
 
 

@@ -12,6 +12,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
 int ovl_build_index(ovlb_ctx *c);
 int ovl_seed_ref_batch(ovlb_ctx *c);
 int ovl_extend_pairs(ovlb_ctx *c);
+int ovl_prepare_ext_scratch(ovlb_ctx *c);
 int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
                        ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
 int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
@@ -178,7 +179,9 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
   c->n_records = 0;
   int rc = ovl_seed_ref_batch(c);
   if (rc) { tt.stop(); return rc; }
+  if (c->n_pairs) { rc = ovl_prepare_ext_scratch(c); if (rc) { tt.stop(); return rc; } }   // allocation stays outside the kernel's bracket
   EvT te(c->stream);
+  c->ext_warps_launched = 0;
   rc = ovl_extend_pairs(c);
   if (rc) { te.stop(); tt.stop(); return rc; }
   unsigned long long w[4] = {0, 0, 0, 0}, flags = 0;
@@ -186,6 +189,7 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
   CK(cudaMemcpyAsync(&flags, &c->d_counters->v[CT_ERR_FLAGS], 8, cudaMemcpyDeviceToHost, c->stream));
   cudaError_t e = cudaStreamSynchronize(c->stream);
   c->timings.extend_ms = te.stop();
+  c->host_counters[CT_EXT_CAPACITY] += (unsigned long long)((double)c->ext_warps_launched * (double)c->timings.extend_ms * 1e6);
   c->timings.total_ms = tt.stop();
   if (e != cudaSuccess) { ovl_set_error(std::string("extension kernel failed: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; }
   if (flags) {
@@ -205,7 +209,7 @@ int ovlb_fetch_records(ovlb_ctx *c, ovlb_record *out, uint64_t out_cap, uint64_t
   if (c->n_records > out_cap) { ovl_set_error("ovlb_fetch_records: output buffer too small"); return OVLB_ERR_CAPACITY; }
   if (c->n_records && !out) { ovl_set_error("ovlb_fetch_records: null output"); return OVLB_ERR_ARG; }
   EvT t(c->stream);
-  if (c->n_records) CK(cudaMemcpyAsync(out, c->d_records, c->n_records * sizeof(ovlb_record), cudaMemcpyDeviceToHost, c->stream));
+  if (c->n_records) CK(cudaMemcpyAsync(out, c->d_records, c->n_records * sizeof(ovlb_record), cudaMemcpyDefault, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->timings.download_ms = t.stop();
   return OVLB_OK;
@@ -232,6 +236,7 @@ int ovlb_get_counters(ovlb_ctx *c, ovlb_counters *out) {
   out->extend_calls = h.v[CT_EXT_CALLS]; out->dp_cells = h.v[CT_DP_CELLS]; out->hash_kmers = h.v[CT_HASH_KMERS];
   out->ref_kmers = h.v[CT_REF_KMERS]; out->seed_hits = h.v[CT_SEED_HITS]; out->seed_runs = h.v[CT_SEED_RUNS];
   out->pairs = h.v[CT_PAIRS];
+  out->ext_busy_ns = h.v[CT_EXT_BUSY]; out->ext_capacity_ns = c->host_counters[CT_EXT_CAPACITY];
   out->hash_kmers += c->host_counters[CT_HASH_KMERS];
   out->ref_kmers  += c->host_counters[CT_REF_KMERS];
   out->seed_runs  += c->host_counters[CT_SEED_RUNS];

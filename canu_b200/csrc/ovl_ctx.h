@@ -57,12 +57,14 @@ struct DevIndex {
 };
 
 struct DevCounters {              // mirrors ovlb_counters; device-resident, atomically updated
-  unsigned long long v[16];
+  unsigned long long v[24];
 };
 enum {
   CT_HITS_WITHOUT = 0, CT_HITS_WITH, CT_HITS_SKIPPED, CT_MULTI, CT_TOTAL, CT_CONTAINED, CT_DOVETAIL,
   CT_EXT_CALLS, CT_DP_CELLS, CT_HASH_KMERS, CT_REF_KMERS, CT_SEED_HITS, CT_SEED_RUNS, CT_PAIRS,
   CT_ERR_FLAGS /* bit0: run buffer overflow, bit1: record overflow, bit2: arena overflow */,
+  CT_EXT_BUSY /* ns the extension warps spent between their first and their last pair, summed over warps */,
+  CT_EXT_CAPACITY /* host only: launched warps x kernel duration, ns */,
   CT_N
 };
 
@@ -146,11 +148,12 @@ struct ovlb_ctx {
   uint64_t  seed_cap = 0;
   ovlb_record *d_records = nullptr;  uint64_t rec_cap = 0;  uint64_t n_records = 0;
   unsigned long long *d_work = nullptr;   // [8] device-side cursors and counts
-  unsigned long long host_counters[16] = {0};   // counters known on the host (added to the device ones on readout)
+  unsigned long long host_counters[24] = {0};   // counters known on the host (added to the device ones on readout)
 
   ovlb_timings timings;
   cudaEvent_t  ev_start = nullptr, ev_stop = nullptr;     // ovlb_timer_start / ovlb_timer_stop
   uint64_t     launches = 0;
+  uint64_t     ext_warps_launched = 0;             // warps of the last k_extend_pairs launch (0: none)
   bool         staged = false;
 };
 

@@ -621,6 +621,8 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, co
   const DevParams &P = sh_params();
   WarpCtl &C = sh_ctl();
   unsigned long long *err_flags = &counters[CT_ERR_FLAGS];
+  unsigned long long t_begin;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
 
   while (true) {
     unsigned long long pi = 0;
@@ -735,6 +737,9 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, co
     if (C.c_dove)    atomicAdd(&counters[CT_DOVETAIL], C.c_dove);
     if (C.cells)     atomicAdd(&counters[CT_DP_CELLS], C.cells);
     if (C.calls)     atomicAdd(&counters[CT_EXT_CALLS], C.calls);
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    atomicAdd(&counters[CT_EXT_BUSY], t_end - t_begin);
   }
 }
 
@@ -861,6 +866,7 @@ int ovl_extend_pairs(ovlb_ctx *c) {
   if (min_blocks == 2) EXT_LAUNCH(2); else if (min_blocks == 4) EXT_LAUNCH(4); else EXT_LAUNCH(3);
 #undef EXT_LAUNCH
   c->launches++;
+  c->ext_warps_launched = (uint64_t)blocks * EXT_WARPS;
   CK(cudaGetLastError());
   return OVLB_OK;
 }

@@ -250,6 +250,63 @@ int ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ola
   return OVLB_OK;
 }
 
+//  Cost-balanced cut of one hash block's ref range ("when #hash blocks < #GPUs replicate the hash block on
+//  every GPU and split the REF RANGE N ways").  Only refID < hashID pairs are computed (Find_Overlaps.C:279,320), so a ref
+//  read meets only the hash reads behind it: the work of ref read r is ~ len_r x (hash bases with ID > r), a triangle,
+//  and equal-BASE ref blocks (what partitionLength() cuts) are unequal work.  This cuts [ref_bgn, min(ref_end,
+//  hash_end - 1)] into n_parts contiguous tiles of equal estimated work, so that each GPU runs ONE launch per hash block
+//  (an extension launch cannot end before its slowest pair: few large launches beat many small ones).
+int ovlb_plan_balanced(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
+                       uint32_t hash_bgn, uint32_t hash_end, uint32_t ref_bgn, uint32_t ref_end,
+                       uint32_t n_parts, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out) {
+  if (!read_len || !n_out || n_parts == 0) { ovl_set_error("ovlb_plan_balanced: bad argument"); return OVLB_ERR_ARG; }
+  if (hash_bgn < 1) hash_bgn = 1;
+  if (ref_bgn < 1) ref_bgn = 1;
+  if (hash_end > n_reads) hash_end = n_reads;
+  if (ref_end > n_reads) ref_end = n_reads;
+  if (hash_end > 0 && ref_end > hash_end - 1) ref_end = hash_end - 1;
+  *n_out = 0;
+  if (hash_end < hash_bgn || ref_end < ref_bgn) return OVLB_OK;
+  auto usable = [&](uint32_t id) -> uint64_t { return read_len[id] >= min_olap_len ? read_len[id] : 0; };
+  uint64_t hashBases = 0;
+  for (uint32_t id = hash_bgn; id <= hash_end; id++) hashBases += usable(id) ? usable(id) + 1 : 0;
+  //  behind[r] = hash bases with ID > r, accumulated from the top
+  std::vector<double> w(ref_end - ref_bgn + 1);
+  {
+    uint64_t behind = 0;
+    uint32_t h = hash_end;
+    for (uint32_t r = ref_end; ; r--) {
+      while (h > r && h >= hash_bgn) { behind += usable(h); h--; }
+      //  lookup ~ 2 orientations of the read; extension ~ read bases x share of the hash bases it can pair with
+      const double share = hashBases ? (double)behind / (double)hashBases : 0.0;
+      w[r - ref_bgn] = (double)usable(r) * (2.0 / 8.0 + share);
+      if (r == ref_bgn) break;
+    }
+  }
+  double total = 0; for (double x : w) total += x;
+  uint64_t n = 0;
+  uint32_t beg = ref_bgn;
+  double acc = 0;
+  for (uint32_t part = 0; part < n_parts && beg <= ref_end; part++) {
+    const double target = total * (double)(part + 1) / (double)n_parts;
+    uint32_t end = beg;
+    acc += w[end - ref_bgn];
+    while (end < ref_end && (part + 1 == n_parts || acc + 0.5 * w[end + 1 - ref_bgn] < target)) { end++; acc += w[end - ref_bgn]; }
+    if (out) {
+      if (n >= out_cap) { ovl_set_error("ovlb_plan_balanced: output buffer too small"); return OVLB_ERR_CAPACITY; }
+      ovlb_tile &t = out[n];
+      t.hash_bgn = hash_bgn; t.hash_end = hash_end; t.ref_bgn = beg; t.ref_end = end;
+      t.hash_bases = hashBases; t.ref_bases = 0; t.cost = 0;
+      for (uint32_t id = beg; id <= end; id++) { t.ref_bases += usable(id); t.cost += w[id - ref_bgn]; }
+      t.has_hash_reads = hashBases != 0;
+    }
+    n++;
+    beg = end + 1;
+  }
+  *n_out = n;
+  return OVLB_OK;
+}
+
 //  Longest-processing-time-first assignment of tiles to workers: tiles sorted by cost
 //  descending, each given to the currently least-loaded worker.  Deterministic (ties: lower index first).
 int ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner) {

@@ -122,6 +122,8 @@ typedef struct {
   uint64_t seed_hits;         /* exact k-mer hits (Add_Ref calls in the reference)            */
   uint64_t seed_runs;         /* maximal diagonal runs those hits collapse into               */
   uint64_t pairs;             /* oriented candidate read pairs                                */
+  uint64_t ext_busy_ns;       /* extension kernel: time its warps spent working, summed over warps (globaltimer)   */
+  uint64_t ext_capacity_ns;   /* extension kernel: launched warps x kernel duration; busy/capacity = 1 - tail loss  */
 } ovlb_counters;
 
 /*  Per-stage device times of the last ovlb_build_index / ovlb_overlap_ref_batch
@@ -165,7 +167,7 @@ int  ovlb_overlap_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads,
  *  ovlb_fetch_records copies the records out.  */
 int  ovlb_stage_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads);
 int  ovlb_run_staged(ovlb_ctx *ctx, uint64_t *n_records);
-int  ovlb_fetch_records(ovlb_ctx *ctx, ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
+int  ovlb_fetch_records(ovlb_ctx *ctx, ovlb_record *out, uint64_t out_cap, uint64_t *n_out);   /* out: host OR device memory (UVA) */
 
 int  ovlb_get_counters(ovlb_ctx *ctx, ovlb_counters *out);
 int  ovlb_reset_counters(ovlb_ctx *ctx);
@@ -263,6 +265,14 @@ int  ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ol
                      uint64_t hash_block_len, uint64_t ref_block_len,
                      uint32_t hash_min, uint32_t hash_max, uint32_t ref_min, uint32_t ref_max,
                      int strict_reference, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
+/*  Cost-balanced cut of ONE hash block's ref range into n_parts contiguous tiles (at most; fewer when the range holds
+ *  fewer reads).  Only refID < hashID pairs are computed (overlapInCore-Find_Overlaps.C:279,320), so the work of ref read r
+ *  is ~ len_r x (hash bases with ID > r); equal-base blocks (overlapInCorePartition.C:204-226) are unequal work.  Used
+ *  when a job has fewer hash blocks than GPUs: every GPU indexes the hash block and takes one part.
+ *  With out == NULL only counts.  */
+int  ovlb_plan_balanced(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
+                        uint32_t hash_bgn, uint32_t hash_end, uint32_t ref_bgn, uint32_t ref_end,
+                        uint32_t n_parts, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
 /*  owner[i] in [0, n_workers): longest-processing-time-first on tiles[i].cost, deterministic.  */
 int  ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner);
 

@@ -79,3 +79,34 @@ def test_tiles_over_two_gloo_ranks_reproduce_the_single_tile(tmp_path):
     assert min(res["tiles_per_rank"]) > 0
     assert res["records_match_golden"], res
     assert res["stats_match_golden"], res
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 4, 8])
+def test_balanced_ref_cut_covers_once_and_is_balanced(parts):
+    """ovlb_plan_balanced: the ref range of one hash block is cut into contiguous tiles that cover every (ref < hash)
+    pair exactly once and whose TRUE triangular work (ref bases x hash bases behind the ref read) is even."""
+    from canu_b200 import api
+    lens = _lens("A")
+    n = len(lens)
+    tiles = api.plan_balanced(lens, 500, parts)
+    assert len(tiles) == parts
+    assert tiles[0]["ref_bgn"] == 1 and tiles[-1]["ref_end"] == n - 1
+    for a, b in zip(tiles, tiles[1:]):
+        assert b["ref_bgn"] == a["ref_end"] + 1
+    L = np.array([0] + [x if x >= 500 else 0 for x in lens], dtype=np.float64)
+    behind = np.concatenate([np.cumsum(L[::-1])[::-1][1:], [0.0]])      # hash bases with ID > r
+    work = L * behind
+    per = np.array([work[t["ref_bgn"]:t["ref_end"] + 1].sum() for t in tiles])
+    assert per.max() <= per.mean() * 1.15 + work.max()
+    own = api.assign_tiles(tiles, parts)
+    assert sorted(own) == list(range(parts))                # one tile per worker
+
+
+def test_balanced_ref_cut_subranges_and_degenerate():
+    from canu_b200 import api
+    lens = _lens("A")
+    t = api.plan_balanced(lens, 500, 4, hash_range=(50, 120), ref_range=(10, 200))
+    assert t[0]["ref_bgn"] == 10 and t[-1]["ref_end"] == 119 and all(x["hash_bgn"] == 50 and x["hash_end"] == 120 for x in t)
+    assert api.plan_balanced(lens, 500, 4, hash_range=(5, 5), ref_range=(5, 9)) == []
+    few = api.plan_balanced(lens, 500, 8, hash_range=(1, 4), ref_range=(1, 4))
+    assert 1 <= len(few) <= 3 and few[-1]["ref_end"] == 3
