@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--hifi-steps", type=int, default=5)
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the steps of the end-to-end (host buffers) timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate", default="", help="tuning only: 'W:r' runs rank r's tile of a W-way split on this one GPU (no NCCL); not a bench line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -267,9 +268,13 @@ def main():
     max_len = max(lens)
 
     # the job's tile grid: one hash block (everything fits HBM), ref range cut into `world` cost-balanced tiles
-    tiles = api.plan_balanced(lens, MINLEN, world)
-    owner = api.assign_tiles(tiles, world)
-    mine = [t for t, o in zip(tiles, owner) if o == rank]
+    plan_world, plan_rank = world, rank
+    if args.emulate:
+        plan_world, plan_rank = (int(x) for x in args.emulate.split(":"))
+        args.hifi_genome = 0; args.no_cpu_baseline = True
+    tiles = api.plan_balanced(lens, MINLEN, plan_world)
+    owner = api.assign_tiles(tiles, plan_world)
+    mine = [t for t, o in zip(tiles, owner) if o == plan_rank]
     assert len(mine) <= 1, "one launch per GPU and hash block"
     prm = api.OverlapParams(kmer_len=K, max_erate=ERATE, min_olap_len=MINLEN, max_read_len=max_len)
     ov = api.Overlapper(prm, device=local_rank)
@@ -427,7 +432,7 @@ def main():
     peaks, which = measured_peaks()
     line = {
         "metric": "ovl read-pairs aligned/sec", "value": pairs_all / (ms_step * 1e-3), "unit": "read-pairs/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "n_gpus": world, **({"emulated_rank_of_world": args.emulate} if args.emulate else {}), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": config,
         "e2e": {"value": pairs_all / (e2e_step_ms * 1e-3), "unit": "read-pairs/s",

@@ -73,7 +73,7 @@ PAIR_DTYPE = np.dtype([("ref_id", "<u4"), ("hash_id", "<u4"), ("dir", "<i4"), ("
 SEED_DTYPE = np.dtype([("start", "<i4"), ("offset", "<i4"), ("len", "<i4")])
 
 EXPORTS = [
-    "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
+    "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_device_total_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
@@ -115,7 +115,7 @@ def load_library():
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
     L.ovlb_debug_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_params_init.argtypes = [C.POINTER(_Params), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.ovlb_params_free.argtypes = [C.POINTER(_Params)]
@@ -384,7 +384,7 @@ def plan_tiles(read_lens, min_olap_len, hash_block_len, ref_block_len, hash_rang
     return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
 
 
-def plan_balanced(read_lens, min_olap_len, n_parts, hash_range=None, ref_range=None):
+def plan_balanced(read_lens, min_olap_len, n_parts, hash_range=None, ref_range=None, lookup_weight=0.002):
     """Cut one hash block's ref range into n_parts contiguous tiles of equal estimated work (ovlb_plan_balanced)."""
     L = load_library()
     n = len(read_lens)
@@ -394,7 +394,7 @@ def plan_balanced(read_lens, min_olap_len, n_parts, hash_range=None, ref_range=N
     rb, re_ = ref_range if ref_range else (1, n)
     cnt = C.c_uint64()
     arr = (_Tile * max(n_parts, 1))()
-    _check(L.ovlb_plan_balanced(rl.ctypes.data, n, min_olap_len, hb, he, rb, re_, n_parts, C.cast(arr, C.c_void_p), n_parts, C.byref(cnt)))
+    _check(L.ovlb_plan_balanced(rl.ctypes.data, n, min_olap_len, hb, he, rb, re_, n_parts, float(lookup_weight), C.cast(arr, C.c_void_p), n_parts, C.byref(cnt)))
     return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
 
 

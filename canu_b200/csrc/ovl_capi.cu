@@ -47,6 +47,13 @@ int ovlb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes) 
   return OVLB_OK;
 }
 
+int ovlb_device_total_memory(int device, uint64_t *total_bytes) {
+  cudaDeviceProp prop;
+  if (!total_bytes || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { cudaGetLastError(); ovl_set_error("ovlb_device_total_memory: bad device or no CUDA"); return OVLB_ERR_CUDA; }
+  *total_bytes = prop.totalGlobalMem;
+  return OVLB_OK;
+}
+
 int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   if (!p || !out) { ovl_set_error("ovlb_create: null argument"); return OVLB_ERR_ARG; }
   *out = nullptr;
@@ -130,6 +137,7 @@ void ovlb_destroy(ovlb_ctx *c) {
 int ovlb_load_hash_reads(ovlb_ctx *c, const ovlb_reads *reads) {
   if (!c || !reads) { ovl_set_error("ovlb_load_hash_reads: null argument"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
+  if (reads->n_reads >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
   c->index.built = false;
   c->skip_keys.clear();
   return ovl_upload_reads(c, reads, c->hash, true, &c->timings.upload_ms, &c->timings.encode_ms);
@@ -155,6 +163,7 @@ int ovlb_build_index(ovlb_ctx *c) {
 
 int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
   if (!c || !reads) { ovl_set_error("ovlb_stage_ref_batch: null argument"); return OVLB_ERR_ARG; }
+  if (reads->n_reads >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   CK(cudaSetDevice(c->device));
   c->staged = false;
   int rc = ovl_upload_reads(c, reads, c->ref, false, &c->timings.upload_ms, &c->timings.encode_ms);
@@ -175,15 +184,22 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
     c->timings.upload_ms = ms; c->timings.encode_ms = 0;
     c->ref_pending = false;
   }
+  //  a failed run (buffer overflow -> the caller splits the batch and retries) must not leave its partial counts behind
+  DevCounters snap; unsigned long long hsnap[24];
+  CK(cudaMemcpyAsync(&snap, c->d_counters, sizeof(snap), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(hsnap, c->host_counters, sizeof(hsnap));
+  auto rollback = [&]() { snap.v[CT_ERR_FLAGS] = 0; cudaMemcpyAsync(c->d_counters, &snap, sizeof(snap), cudaMemcpyHostToDevice, c->stream);
+                          cudaStreamSynchronize(c->stream); memcpy(c->host_counters, hsnap, sizeof(hsnap)); };
   EvT tt(c->stream);
   c->n_records = 0;
   int rc = ovl_seed_ref_batch(c);
-  if (rc) { tt.stop(); return rc; }
-  if (c->n_pairs) { rc = ovl_prepare_ext_scratch(c); if (rc) { tt.stop(); return rc; } }   // allocation stays outside the kernel's bracket
+  if (rc) { tt.stop(); rollback(); return rc; }
+  if (c->n_pairs) { rc = ovl_prepare_ext_scratch(c); if (rc) { tt.stop(); rollback(); return rc; } }   // allocation stays outside the kernel's bracket
   EvT te(c->stream);
   c->ext_warps_launched = 0;
   rc = ovl_extend_pairs(c);
-  if (rc) { te.stop(); tt.stop(); return rc; }
+  if (rc) { te.stop(); tt.stop(); rollback(); return rc; }
   unsigned long long w[4] = {0, 0, 0, 0}, flags = 0;
   CK(cudaMemcpyAsync(w, c->d_work, 32, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(&flags, &c->d_counters->v[CT_ERR_FLAGS], 8, cudaMemcpyDeviceToHost, c->stream));
@@ -193,7 +209,7 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
   c->timings.total_ms = tt.stop();
   if (e != cudaSuccess) { ovl_set_error(std::string("extension kernel failed: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA; }
   if (flags) {
-    cudaMemsetAsync(&c->d_counters->v[CT_ERR_FLAGS], 0, 8, c->stream);
+    rollback();
     ovl_set_error("device buffer overflow in the extension kernel (flags " + std::to_string(flags) + ")");
     return OVLB_ERR_CAPACITY;
   }

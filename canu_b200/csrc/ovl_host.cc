@@ -83,7 +83,7 @@ int ovlb_params_init(ovlb_params *p, uint32_t kmer_len, double max_erate, double
                      int partial, int unique_per_pair, int min_olap_len, int no_hopeless, int min_kmers,
                      uint32_t max_read_len) {
   if (!p) { ovl_set_error("ovlb_params_init: null"); return OVLB_ERR_ARG; }
-  if (kmer_len < 2 || kmer_len > 31) { ovl_set_error("ovlb_params_init: kmer_len must be in 2..31"); return OVLB_ERR_ARG; }
+  if (kmer_len < 2 || kmer_len > 30) { ovl_set_error("ovlb_params_init: kmer_len must be in 2..30 (k-mer + 3 class bits + 1 sentinel bit must fit 64 bits)"); return OVLB_ERR_ARG; }
   if (!(max_erate > 0.0) || max_erate >= 1.0) { ovl_set_error("ovlb_params_init: max_erate must be in (0,1)"); return OVLB_ERR_ARG; }
   if (align_noise == 0.0) align_noise = 1.0;
   memset(p, 0, sizeof(*p));
@@ -167,7 +167,7 @@ const ovlb_reads *ovlb_reads_view(const ovlb_reads_owner *o) { return o ? &o->vi
 void ovlb_reads_free(ovlb_reads_owner *o) { delete o; }
 
 int ovlb_kmer_keys(const char *kmer, uint32_t kmer_len, uint64_t *fwd_key, uint64_t *rc_key) {
-  if (!kmer || !fwd_key || !rc_key || kmer_len < 2 || kmer_len > 31) { ovl_set_error("ovlb_kmer_keys: bad argument"); return OVLB_ERR_ARG; }
+  if (!kmer || !fwd_key || !rc_key || kmer_len < 2 || kmer_len > 30) { ovl_set_error("ovlb_kmer_keys: bad argument (kmer_len must be in 2..30)"); return OVLB_ERR_ARG; }
   uint64_t f = 0, r = 0;
   for (uint32_t j = 0; j < kmer_len; j++) {
     uint64_t code;
@@ -258,8 +258,8 @@ int ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ola
 //  (an extension launch cannot end before its slowest pair: few large launches beat many small ones).
 int ovlb_plan_balanced(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
                        uint32_t hash_bgn, uint32_t hash_end, uint32_t ref_bgn, uint32_t ref_end,
-                       uint32_t n_parts, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out) {
-  if (!read_len || !n_out || n_parts == 0) { ovl_set_error("ovlb_plan_balanced: bad argument"); return OVLB_ERR_ARG; }
+                       uint32_t n_parts, double lookup_weight, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out) {
+  if (!read_len || !n_out || n_parts == 0 || !(lookup_weight >= 0.0)) { ovl_set_error("ovlb_plan_balanced: bad argument"); return OVLB_ERR_ARG; }
   if (hash_bgn < 1) hash_bgn = 1;
   if (ref_bgn < 1) ref_bgn = 1;
   if (hash_end > n_reads) hash_end = n_reads;
@@ -277,9 +277,9 @@ int ovlb_plan_balanced(const uint32_t *read_len, uint32_t n_reads, uint32_t min_
     uint32_t h = hash_end;
     for (uint32_t r = ref_end; ; r--) {
       while (h > r && h >= hash_bgn) { behind += usable(h); h--; }
-      //  lookup ~ 2 orientations of the read; extension ~ read bases x share of the hash bases it can pair with
+      //  lookup ~ the read's bases (both orientations); extension ~ read bases x share of the hash bases it can pair with
       const double share = hashBases ? (double)behind / (double)hashBases : 0.0;
-      w[r - ref_bgn] = (double)usable(r) * (2.0 / 8.0 + share);
+      w[r - ref_bgn] = (double)usable(r) * (lookup_weight + share);
       if (r == ref_bgn) break;
     }
   }

@@ -1032,7 +1032,11 @@ static int ensure(T *&ptr, size_t &cap, size_t need, size_t slack_num = 5, size_
   if (ptr) { cudaFree(ptr); ptr = nullptr; cap = 0; }
   size_t n = need * slack_num / slack_den + 64;
   cudaError_t e = cudaMalloc((void **)&ptr, n * sizeof(T));
-  if (e != cudaSuccess) { ovl_set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); cudaGetLastError(); return OVLB_ERR_CUDA; }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation) { ovl_set_error("device memory exhausted (" + std::to_string(n * sizeof(T)) + " bytes wanted): use a smaller hash block / ref batch"); return OVLB_ERR_CAPACITY; }
+    ovl_set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); return OVLB_ERR_CUDA;
+  }
   cap = n;
   return OVLB_OK;
 }
@@ -1190,7 +1194,7 @@ int ovl_build_index(ovlb_ctx *c) {
 
     if (bucketed) {
       //  number of buckets: a power of two with ~BK_TARGET tuples each, cut out of the top bits of the 2K+3-bit key
-      int B = 8; while (B < 2 * K && (nt >> B) > BK_TARGET) B++;
+      int B = 2 * K + 3 < 8 ? 2 * K + 3 : 8; while (B < 2 * K && (nt >> B) > BK_TARGET) B++;
       const uint32_t nb = 1u << B;
       const int shift = 2 * K + 3 - B;
       const uint64_t tmp_cap = nt / 4 * 3 + (1u << 20);

@@ -241,6 +241,8 @@ int main(int argc, char **argv) {
     else if (!strcmp(a, "--hashbits"))    need(a);
     else if (!strcmp(a, "--hashdatalen")) need(a);
     else if (!strcmp(a, "--hashload"))    need(a);
+    else if (!strcmp(a, "--readsperbatch"))  need(a);                    // reference work-distribution knobs (overlapInCore.C:352-356): no effect on output
+    else if (!strcmp(a, "--readsperthread")) need(a);
     else if (!strcmp(a, "-o"))            G.outName = need(a);
     else if (!strcmp(a, "-s"))            G.statName = need(a);
     else if (!strcmp(a, "-t"))            need(a);
@@ -260,13 +262,14 @@ int main(int argc, char **argv) {
     else if (!strcmp(a, "--refbatch"))    G.refBatchBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--hashblock"))   G.hashBlockBases = strtoull(need(a), nullptr, 10);
     else if (!strcmp(a, "--version"))     { printf("overlapInCore (canu_b200, B200-native ovl) for canu v2.3\n"); return 0; }
+    else if (a[0] == '-' && a[1] != 0)    { fprintf(stderr, "Unknown option '%s'\n", a); err++; }
     else if (G.storePath == nullptr)      G.storePath = a;
     else { fprintf(stderr, "Unknown option '%s'\n", a); err++; }
   }
   if (G.kmerLen == 0)       { fprintf(stderr, "* No kmer length supplied; -k needed!\n"); err++; }
   if (G.outName == nullptr) { fprintf(stderr, "ERROR:  No output file name specified\n"); err++; }
   if (err || G.storePath == nullptr) { usage(argv[0]); return 1; }
-  if (G.kmerLen > 31) FAIL("ERROR: k-mer length %lu is too large (max 31)", (unsigned long)G.kmerLen);
+  if (G.kmerLen < 2 || G.kmerLen > 30) FAIL("ERROR: k-mer length %lu is out of range (2..30)", (unsigned long)G.kmerLen);
 
   auto t_start = std::chrono::steady_clock::now();
 
@@ -354,7 +357,20 @@ int main(int argc, char **argv) {
 
   //  Re-block the job inside the process (the output does not depend on blocking): hash blocks
   //  sized for HBM, ref batches sized for the device seed buffers -- and small enough that every GPU gets several.
-  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : 1500000000ull;
+  //  Hash block from the memory a context gets: ovlb_build_index needs, per hash base, 1 B of dp4 reads (both
+  //  orientations) + 24 B of tuple scratch (key, partitioned key, position, occurrence) and, per DISTINCT k-mer, ~120 B
+  //  (slot, scratch slot, two 16 B table entries at load 0.5, path-sort pairs) -- and in a large job most k-mers of a
+  //  block are distinct (a block covers the genome a few times at most), so the model is ~150 B per base.  The ref
+  //  batch, the seed buffers and the extension scratch share the other half of the budget.
+  uint64_t minBudget = ~0ull;
+  for (uint32_t wi = 0; wi < (uint32_t)G.gpus.size(); wi++) {
+    const int d = G.gpus[wi];
+    uint64_t tot = 0;                                                   // total, not free: asking for free memory would create the
+    if (ovlb_device_total_memory(d, &tot)) FAIL("ERROR: %s", ovlb_last_error());   // device's context here, serially over the GPUs
+    minBudget = std::min<uint64_t>(minBudget, (uint64_t)((double)tot * 0.95 * 0.8 / sharers[wi]));
+  }
+  const uint64_t hashBlockModel = std::max<uint64_t>(minBudget / 2 / 150, 1000000ull);
+  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : std::min<uint64_t>(1500000000ull, hashBlockModel);
   uint64_t refBatch = G.refBatchBases ? G.refBatchBases : 256000000ull;
   //  Several workers: every one should get a few tiles of each hash block so that longest-first assignment can balance
   //  them, but not many small ones -- an extension launch cannot end before its slowest pair does (0.2 - 1 s on noisy
@@ -373,10 +389,74 @@ int main(int argc, char **argv) {
         FAIL("ERROR: %s", ovlb_last_error());
     }
   }
+  //  Fewer hash blocks than twice the workers (small and medium jobs; always the case when the job fits one block): every
+  //  worker indexes every hash block and takes ONE cost-balanced part of its ref range -- an extension
+  //  launch cannot end before its slowest pair, so few large launches beat the many small tiles LPT would need, and the
+  //  triangular refID < hashID rule makes equal-base tiles unequal work (ovlb_plan_balanced).  A part larger than the
+  //  device's ref batch is cut further, all pieces staying with the same worker.
+  std::vector<int32_t> fixedOwner;
+  if (W > 1 && !tiles.empty()) {
+    std::vector<std::pair<uint32_t, uint32_t>> blocks;
+    for (const ovlb_tile &T : tiles) if (blocks.empty() || blocks.back().first != T.hash_bgn) blocks.push_back({T.hash_bgn, T.hash_end});
+    if (blocks.size() < 2 * (size_t)W) {
+      const double lookupWeight = G.maxErate >= 0.03 ? 0.01 : 0.6;
+      const uint64_t maxPiece = G.refBatchBases ? G.refBatchBases : 256000000ull;
+      std::vector<ovlb_tile> bal;
+      for (auto &hb : blocks) {
+        std::vector<ovlb_tile> parts(W);
+        uint64_t np2 = 0;
+        if (ovlb_plan_balanced(readLen.data(), N, 0, hb.first, hb.second, G.bgnRefID, G.endRefID, W, lookupWeight, parts.data(), W, &np2)) FAIL("ERROR: %s", ovlb_last_error());
+        for (uint64_t pi = 0; pi < np2; pi++) {
+          const ovlb_tile &Pt = parts[pi];
+          const uint32_t pieces = (uint32_t)std::max<uint64_t>(1, (Pt.ref_bases + maxPiece - 1) / maxPiece);
+          const uint64_t per = Pt.ref_bases / pieces + 1;
+          uint32_t b = Pt.ref_bgn;
+          while (b <= Pt.ref_end) {
+            uint64_t acc = 0; uint32_t e2 = b;
+            while (e2 < Pt.ref_end && acc + readLen[e2] < per) { acc += readLen[e2]; e2++; }
+            ovlb_tile Q = Pt; Q.ref_bgn = b; Q.ref_end = e2; Q.ref_bases = 0;
+            for (uint32_t id = b; id <= e2; id++) Q.ref_bases += readLen[id];
+            Q.cost = Pt.cost * (double)Q.ref_bases / (double)std::max<uint64_t>(Pt.ref_bases, 1);
+            bal.push_back(Q); fixedOwner.push_back((int32_t)pi);
+            b = e2 + 1;
+          }
+        }
+      }
+      tiles.swap(bal);
+    }
+  }
+  //  The device keys a seed run by (ref read:18 bits | hash read:24 bits): cut ref ranges of more than 200 000 reads up
+  //  front (short-read stores), and refuse hash blocks of more than 2^24 - 1 reads with a usable message.
+  {
+    std::vector<ovlb_tile> cut;
+    std::vector<int32_t> cutOwner;
+    for (size_t ti = 0; ti < tiles.size(); ti++) {
+      const ovlb_tile &T = tiles[ti];
+      const int32_t fo = fixedOwner.empty() ? -1 : fixedOwner[ti];
+      if (T.hash_end - T.hash_bgn + 1 >= (1u << 24))
+        FAIL("ERROR: hash block %u-%u holds more than 16777215 reads; use a smaller --hashblock", T.hash_bgn, T.hash_end);
+      const uint32_t maxRef = 200000;
+      if (T.ref_end - T.ref_bgn + 1 <= maxRef) { cut.push_back(T); cutOwner.push_back(fo); continue; }
+      const uint32_t pieces = (T.ref_end - T.ref_bgn + maxRef) / maxRef;
+      for (uint32_t b = T.ref_bgn; b <= T.ref_end; ) {
+        const uint32_t e2 = (uint32_t)std::min<uint64_t>(T.ref_end, (uint64_t)b + maxRef - 1);
+        ovlb_tile P2 = T; P2.ref_bgn = b; P2.ref_end = e2;
+        P2.ref_bases = 0; for (uint32_t id = b; id <= e2; id++) P2.ref_bases += readLen[id];
+        P2.cost = T.cost / pieces;
+        cut.push_back(P2); cutOwner.push_back(fo);
+        if (e2 == T.ref_end) break;
+        b = e2 + 1;
+      }
+    }
+    tiles.swap(cut);
+    if (!fixedOwner.empty()) fixedOwner.swap(cutOwner);
+  }
   //  owner of every tile: whole hash blocks per GPU when there are plenty of them (no index is built twice),
   //  else tile by tile (the hash block is then indexed on every GPU that got one of its tiles)
   std::vector<uint32_t> owner(tiles.size(), 0);
-  if (W > 1 && !tiles.empty()) {
+  if (!fixedOwner.empty()) {
+    for (size_t i = 0; i < tiles.size(); i++) owner[i] = (uint32_t)fixedOwner[i];
+  } else if (W > 1 && !tiles.empty()) {
     std::vector<ovlb_tile> blocks;                                     // one pseudo-tile per hash block, cost summed
     std::vector<size_t> blockOf(tiles.size());
     for (size_t i = 0; i < tiles.size(); i++) {
@@ -468,7 +548,7 @@ int main(int argc, char **argv) {
         first = false;
         ph.pack_ref += now_s() - t0; t0 = now_s();
         uint64_t n = 0;
-        int rc = (r2 - rb + 1 > 200000) ? OVLB_ERR_CAPACITY : ovlb_stage_ref_batch(ctx, &RB.view);
+        int rc = ovlb_stage_ref_batch(ctx, &RB.view);
         ph.stage += now_s() - t0; t0 = now_s();
         if (!rc) rc = ovlb_run_staged(ctx, &n);
         ph.run += now_s() - t0; t0 = now_s();

@@ -141,6 +141,9 @@ int  ovlb_device_count(void);
  *  split the memory between them through ovlb_params.device_mem_budget.  */
 int  ovlb_device_memory(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 
+/*  Total HBM of a device from its properties: does not create a context on it (cheap on a multi-GPU node).  */
+int  ovlb_device_total_memory(int device, uint64_t *total_bytes);
+
 int  ovlb_create(int device, const ovlb_params *params, ovlb_ctx **out);
 void ovlb_destroy(ovlb_ctx *ctx);
 
@@ -269,10 +272,13 @@ int  ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ol
  *  fewer reads).  Only refID < hashID pairs are computed (overlapInCore-Find_Overlaps.C:279,320), so the work of ref read r
  *  is ~ len_r x (hash bases with ID > r); equal-base blocks (overlapInCorePartition.C:204-226) are unequal work.  Used
  *  when a job has fewer hash blocks than GPUs: every GPU indexes the hash block and takes one part.
+ *  lookup_weight = cost of looking one ref base up (probe + seeding, which does not depend on the hash IDs) relative to
+ *  extending it against the WHOLE hash block: measured ~0.6 on HiFi-like reads at --maxerate 0.01 (C2: lookup 17.6 ms,
+ *  extension 15.5 ms for half the pairs), ~0.002 at --maxerate 0.06 where the extension is > 99 % of the time.
  *  With out == NULL only counts.  */
 int  ovlb_plan_balanced(const uint32_t *read_len, uint32_t n_reads, uint32_t min_olap_len,
                         uint32_t hash_bgn, uint32_t hash_end, uint32_t ref_bgn, uint32_t ref_end,
-                        uint32_t n_parts, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
+                        uint32_t n_parts, double lookup_weight, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
 /*  owner[i] in [0, n_workers): longest-processing-time-first on tiles[i].cost, deterministic.  */
 int  ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_workers, uint32_t *owner);
 
