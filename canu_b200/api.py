@@ -115,7 +115,7 @@ def load_library():
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
     L.ovlb_debug_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-    L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_params_init.argtypes = [C.POINTER(_Params), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.ovlb_params_free.argtypes = [C.POINTER(_Params)]
@@ -131,7 +131,7 @@ def load_library():
                                   C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_assign_tiles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
     L.ovlb_plan_balanced.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                     C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+                                     C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     _LIB = L
     return L
 
