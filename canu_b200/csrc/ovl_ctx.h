@@ -85,8 +85,7 @@ struct ExtScratch {
   uint64_t  arena_cap = 0;        // uint2 entries per warp
   uint32_t  gring_cap = 0;        // ints per global ring (power of two)
   uint2    *arena = nullptr;      // [n_warps][arena_cap]   from-code bit planes
-  int32_t  *row_left = nullptr;   // [n_warps][emax+2]
-  uint32_t *row_off = nullptr;    // [n_warps][emax+2]
+  int2     *row_meta = nullptr;   // [n_warps][emax+2]  (leftmost diagonal of the row, first arena word of the row)
   int32_t  *gring = nullptr;      // [n_warps][2][gring_cap]
   uint8_t  *path = nullptr;       // [n_warps][emax+2]
   int32_t  *ival = nullptr;       // [n_warps][emax+2]

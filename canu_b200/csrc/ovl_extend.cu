@@ -27,6 +27,8 @@
 #define EXT_WARPS  8
 #define EXT_THREADS (EXT_WARPS * 32)
 #define SRING      512                    // ints per shared ring (per row, per warp)
+#define SRING_PAD  64                     // slack behind every ring: the branch-free cell front reads predecessors of masked lanes
+#define SRING_STRIDE (SRING + SRING_PAD)
 #define FULL       0xffffffffu
 
 struct DpOut { int a_end, t_end, errors, leftover, match_to_end, delta_len; };
@@ -38,7 +40,7 @@ struct DpOut { int a_end, t_end, errors, leftover, match_to_end, delta_len; };
 struct WarpCtl {
   int      *gring0, *gring1;              // HBM rings (bands wider than the shared ring)
   uint2    *arena;                        // from-code bit planes
-  int32_t  *row_left; uint32_t *row_off;
+  int2     *row_meta;                     // per row: (leftmost diagonal, first arena word)
   uint8_t  *path; int32_t *ival; uint32_t *ikc;
   int32_t  *ldelta, *rdelta;
   uint64_t  arena_cap;
@@ -59,13 +61,13 @@ struct WarpCtl {
 #define EXT_SM_PARAMS 0
 #define EXT_SM_CTL    128
 #define EXT_SM_RINGS  (EXT_SM_CTL + ((EXT_WARPS * (int)sizeof(WarpCtl) + 127) / 128) * 128)
-#define EXT_SM_BYTES  (EXT_SM_RINGS + EXT_WARPS * 2 * SRING * 4)
+#define EXT_SM_BYTES  (EXT_SM_RINGS + EXT_WARPS * 2 * SRING_STRIDE * 4)
 static_assert(sizeof(DevParams) <= EXT_SM_CTL, "DevParams must fit its shared-memory slot");
 extern __shared__ __align__(16) unsigned char ext_sm[];
 
 __device__ __forceinline__ const DevParams &sh_params() { return *reinterpret_cast<const DevParams *>(ext_sm + EXT_SM_PARAMS); }
 __device__ __forceinline__ WarpCtl &sh_ctl() { return reinterpret_cast<WarpCtl *>(ext_sm + EXT_SM_CTL)[threadIdx.x >> 5]; }
-__device__ __forceinline__ int *sh_ring(int which) { return reinterpret_cast<int *>(ext_sm + EXT_SM_RINGS) + ((threadIdx.x >> 5) * 2 + which) * SRING; }
+__device__ __forceinline__ int *sh_ring(int which) { return reinterpret_cast<int *>(ext_sm + EXT_SM_RINGS) + ((threadIdx.x >> 5) * 2 + which) * SRING_STRIDE; }
 
 //  Number of leading positions (< lim) where A[a..] and T[t..] match; all 32 lanes cooperate, 512 bases per round.
 __device__ __forceinline__ int warp_slide(const uint64_t *A, int a, const uint64_t *T, int t, int lim, int lane) {
@@ -115,7 +117,7 @@ __device__ __noinline__ int warp_traceback(const uint64_t *A, int a0, int m, con
                               int e_start, int d_start, int v_start, int row0, bool fwd_rules, int first_code,
                               int32_t *out, int lane) {
   WarpCtl &C = sh_ctl();
-  const int32_t *row_left = C.row_left; const uint32_t *row_off = C.row_off; const uint2 *arena = C.arena;
+  const int2 *row_meta = C.row_meta; const uint2 *arena = C.arena;
   uint8_t *path = C.path; int32_t *ival = C.ival; uint32_t *ikc = C.ikc;
   //  Phase A: walk down, 32 rows per round
   int n_ind = 0;
@@ -124,8 +126,9 @@ __device__ __noinline__ int warp_traceback(const uint64_t *A, int a0, int m, con
     const int kk = kb - lane;                      // my row
     int rl = 0; uint32_t glo = 0; uint2 w0 = make_uint2(0, 0), w1 = w0, w2 = w0;
     if (kk >= 1) {
-      rl = row_left[kk];
-      uint32_t ro = row_off[kk];
+      const int2 rm = row_meta[kk];
+      rl = rm.x;
+      uint32_t ro = (uint32_t)rm.y;
       int idx_lo = dcur - lane - rl; if (idx_lo < 0) idx_lo = 0;
       glo = (uint32_t)idx_lo >> 5;
       const uint2 *ap = arena + ro + glo;
@@ -232,61 +235,111 @@ __device__ __noinline__ int warp_traceback(const uint64_t *A, int a0, int m, con
 //  on its left), so one pass over the row gives Left, Right, Longest and Best_d.
 struct RowOut { int mn, mx, bv, bd, term_d, term_row; };
 
-template <bool SH>
+//  Read bases are only ever read by this kernel: fetch them through the non-coherent path (LDG.E.CONSTANT) -- the
+//  pointers come out of the per-warp control block in shared memory, so the compiler would otherwise emit generic LD.
+__device__ __forceinline__ uint32_t fetch8_nc(const uint32_t *w32, int x) {
+  const uint32_t *p = w32 + (x >> 3);
+  return __funnelshift_r(__ldg(p), __ldg(p + 1), (x & 7) << 2);
+}
+
+//  One cell, front half: predecessor max, slide limit, first 8 bases.
+struct CellState { int row, code, lim, cnt; bool act, more; };
+
+//  Branch-free on purpose: with divergent `if (act)` / `if (lim > 0)` regions the compiler serialises the fronts of the
+//  two groups of an iteration and every load is waited for before the next group starts.  Inactive lanes (past the
+//  right edge of the band: only in a row's last group) compute on row 0 / diagonal 0 and are masked; the rings are
+//  padded so that their three predecessor loads stay in bounds.  lim >= 0 for every active cell (a cell at the end of
+//  A or T ends the extension in its own row), so cnt = min(cnt, lim) also covers lim == 0.
+__device__ __forceinline__ void cell_front(CellState &c, const int *prev, int d, int Ru,
+                                           const uint32_t *A32, int a0, int m, const uint32_t *T32, int t0, int n) {
+  const bool act = d <= Ru;
+  const int a = prev[0], b = prev[1], c2 = prev[2];
+  int row = 1 + b, code = 0;
+  if (a > row) { row = a; code = 1; }
+  if (1 + c2 > row) { row = 1 + c2; code = 2; }
+  row = act ? row : 0;
+  const int dd = act ? d : 0;
+  int lim = min(m - row, n - dd - row);
+  lim = act ? lim : 0;
+  //  every lane slides its own diagonal over the first 8 bases (32-bit arithmetic) ...
+  const int c8 = ovl_match8(fetch8_nc(A32, a0 + row), fetch8_nc(T32, t0 + row + dd));
+  c.act = act; c.row = row; c.code = code; c.lim = lim;
+  c.more = (c8 == 8) && (lim > 8);
+  c.cnt = min(c8, lim);
+}
+
+//  ... and the few diagonals that are still matching (on real overlaps: the true one) are finished by the whole
+//  warp, 512 bases per round, instead of one lane chasing dependent loads
+__device__ __forceinline__ void cell_slides(CellState &c, int d, const uint64_t *A, int a0, const uint64_t *T, int t0, int lane) {
+  for (unsigned pend = __ballot_sync(FULL, c.more); pend; pend &= pend - 1) {
+    const int l = __ffs(pend) - 1;
+    const int r_l = __shfl_sync(FULL, c.row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, c.lim, l);
+    const int ext = warp_slide(A, a0 + r_l + 8, T, t0 + r_l + d_l + 8, lim_l - 8, lane);
+    if (lane == l) c.cnt = 8 + ext;
+  }
+}
+
+//  Back half: store, pruning / best bookkeeping, from-code planes, termination.  Returns true if a cell reached the
+//  end of A or T (cnt == lim <=> row == m or row + d == n, because lim = min(m - row, n - d - row) >= 0).
+__device__ __forceinline__ bool cell_back(const CellState &c, int *cur, int d, int dbase, int lim_e, uint2 *arena_slot, int lane,
+                                          int &mn, int &mx, int &bv, int &bd, RowOut &ro) {
+  const int row = c.row + c.cnt;
+  if (c.act) {
+    cur[0] = row;
+    if (!(row + (d > 0 ? d : 0) < lim_e)) {
+      mn = min(mn, d); mx = max(mx, d);
+      if (row > bv) { bv = row; bd = d; }
+    }
+  }
+  const unsigned b0 = __ballot_sync(FULL, c.act && (c.code & 1));
+  const unsigned b1 = __ballot_sync(FULL, c.act && (c.code >> 1));
+  if (lane == 0) *arena_slot = make_uint2(b0, b1);
+  const unsigned hb = __ballot_sync(FULL, c.act && (c.cnt == c.lim));
+  if (hb) {
+    const int tl = __ffs(hb) - 1;
+    ro.term_d = dbase + tl;
+    ro.term_row = __shfl_sync(FULL, row, tl);
+    return true;
+  }
+  return false;
+}
+
+//  U = groups of 32 cells in flight per iteration: with U = 2 the loads and the dependent max/shift/compare chains of
+//  two groups overlap (ncu: the single-group loop left 24 % of the issue slots empty on long-scoreboard / wait stalls
+//  behind the base fetches at 30 warps per SM).
+template <bool SH, int U>
 __device__ __forceinline__ void dp_row_cells(int psel, int pidx, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                                              int Lu, int Ru, uint32_t ngroups, int lim_e, uint2 *arena_row, int lane, RowOut &ro) {
   const int *prev; int *cur;
-  if (SH) { int *ring = sh_ring(0); prev = ring + psel * SRING; cur = ring + (psel ^ 1) * SRING; }
+  if (SH) { int *ring = sh_ring(0); prev = ring + psel * SRING_STRIDE; cur = ring + (psel ^ 1) * SRING_STRIDE; }
   else    { WarpCtl &C = sh_ctl(); prev = psel ? C.gring1 : C.gring0; cur = psel ? C.gring0 : C.gring1; }
   const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
   int mn = 0x7fffffff, mx = -0x7fffffff, bv = -1, bd = 0x7fffffff;
   ro.term_d = 0x7fffffff; ro.term_row = 0;
   prev += pidx + lane; cur += 2 + lane;
-  for (uint32_t g = 0; g < ngroups; g++, prev += 32, cur += 32) {
-    const int d = Lu + (int)(g << 5) + lane;
-    const bool act = d <= Ru;
-    int row = 0, code = 0, lim = 0, cnt = 0;
-    bool more = false;
-    if (act) {
-      const int a = prev[0], b = prev[1], c2 = prev[2];
-      row = 1 + b;
-      if (a > row) { row = a; code = 1; }
-      if (1 + c2 > row) { row = 1 + c2; code = 2; }
-      lim = min(m - row, n - d - row);
-      if (lim > 0) {
-        //  every lane slides its own diagonal over the first 8 bases (32-bit arithmetic) ...
-        cnt = ovl_match8(ovl_fetch8(A32, a0 + row), ovl_fetch8(T32, t0 + row + d));
-        more = (cnt == 8) && (lim > 8);
-        if (cnt > lim) cnt = lim;
-      }
-    }
-    //  ... and the few diagonals that are still matching (on real overlaps: the true one) are finished by the
-    //  whole warp, 512 bases per round, instead of one lane chasing dependent loads
-    for (unsigned pend = __ballot_sync(FULL, more); pend; pend &= pend - 1) {
-      const int l = __ffs(pend) - 1;
-      const int r_l = __shfl_sync(FULL, row, l), d_l = __shfl_sync(FULL, d, l), lim_l = __shfl_sync(FULL, lim, l);
-      const int ext = warp_slide(A, a0 + r_l + 8, T, t0 + r_l + d_l + 8, lim_l - 8, lane);
-      if (lane == l) cnt = 8 + ext;
-    }
-    if (act) {
-      row += cnt;
-      cur[0] = row;
-      if (!(row + (d > 0 ? d : 0) < lim_e)) {
-        mn = min(mn, d); mx = max(mx, d);
-        if (row > bv) { bv = row; bd = d; }
-      }
-    }
-    const unsigned b0 = __ballot_sync(FULL, act && (code & 1));
-    const unsigned b1 = __ballot_sync(FULL, act && (code >> 1));
-    if (lane == 0) arena_row[g] = make_uint2(b0, b1);
-    const unsigned hb = __ballot_sync(FULL, act && (row == m || row + d == n));
-    if (hb) {
-      const int tl = __ffs(hb) - 1;
-      ro.term_d = Lu + (int)(g << 5) + tl;
-      ro.term_row = __shfl_sync(FULL, row, tl);
-      break;
+  uint32_t g = 0;
+  if (U == 2) {
+    for (; g + 2 <= ngroups; g += 2, prev += 64, cur += 64) {
+      const int dbase = Lu + (int)(g << 5);
+      const int d0 = dbase + lane, d1 = d0 + 32;
+      CellState c0, c1;
+      cell_front(c0, prev, d0, Ru, A32, a0, m, T32, t0, n);
+      cell_front(c1, prev + 32, d1, Ru, A32, a0, m, T32, t0, n);
+      cell_slides(c0, d0, A, a0, T, t0, lane);
+      cell_slides(c1, d1, A, a0, T, t0, lane);
+      if (cell_back(c0, cur, d0, dbase, lim_e, arena_row + g, lane, mn, mx, bv, bd, ro)) goto done;
+      if (cell_back(c1, cur + 32, d1, dbase + 32, lim_e, arena_row + g + 1, lane, mn, mx, bv, bd, ro)) goto done;
     }
   }
+  for (; g < ngroups; g++, prev += 32, cur += 32) {
+    const int dbase = Lu + (int)(g << 5);
+    const int d = dbase + lane;
+    CellState c;
+    cell_front(c, prev, d, Ru, A32, a0, m, T32, t0, n);
+    cell_slides(c, d, A, a0, T, t0, lane);
+    if (cell_back(c, cur, d, dbase, lim_e, arena_row + g, lane, mn, mx, bv, bd, ro)) break;
+  }
+done:
   ro.mn = mn; ro.mx = mx; ro.bv = bv; ro.bd = bd;
 }
 
@@ -302,6 +355,7 @@ __device__ __forceinline__ void dp_row_cells(int psel, int pidx, const uint64_t 
 //  an earlier version called it from four places and, fully inlined, was 17.6 k SASS instructions that spent 79 % of
 //  their stall samples waiting for instruction fetch; as a separate function every memory access re-materialised
 //  its descriptor (R2UR) from the call ABI's vector registers.
+template <int ILP>
 __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
                         int error_limit, bool fwd_rules, unsigned long long *err_flags, int lane) {
   const DevParams &P = sh_params();
@@ -351,15 +405,13 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
     }
     //  generic pointer (rare accesses only), biased so that prev[d] = EA[e-1][d]
     int *prev = (in_shared ? sh_ring(psel) : (psel ? C.gring1 : C.gring0)) + (2 - pbase);
-    if (lane == 0) {
-      prev[L - 1] = -2; prev[L - 2] = -2; prev[R + 1] = -2; prev[R + 2] = -2;
-      C.row_left[e] = Lu; C.row_off[e] = aoff;
-    }
+    if (lane < 4) prev[lane < 2 ? L - 1 - lane : R - 1 + lane] = -2;      // sentinels at L-1, L-2, R+1, R+2: one store
+    if (lane == 4) C.row_meta[e] = make_int2(Lu, (int)aoff);
     __syncwarp();
 
     RowOut ro;
-    if (in_shared) dp_row_cells<true >(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
-    else           dp_row_cells<false>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
+    if (in_shared) dp_row_cells<true, ILP>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
+    else           dp_row_cells<false, 1>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
     const int term_d = ro.term_d, term_row = ro.term_row;
     int mn = ro.mn, mx = ro.mx; const int bv = ro.bv, bd = ro.bd;
     __syncwarp();
@@ -428,6 +480,7 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
 //  Extend_Alignment (prefixEditDistance-extend.C:36-183).  S is the ref read in its search orientation
 //  (S.fwd = oriented sequence, S.rc = its reverse complement); T the hash read.
 //  On return ldelta[0..ldelta_len) (the warp's ldelta scratch) is the merged Left_Delta.
+template <int ILP>
 __device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
                                      int &s_lo, int &s_hi, int &t_lo, int &t_hi, int &errors, int &ldelta_len,
                                      unsigned long long *err_flags, int lane) {
@@ -457,7 +510,7 @@ __device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
     const uint64_t *sw = right ? C.s_fwd : C.s_rc, *tw = right ? C.t_fwd : C.t_rc;
     const int s0 = right ? s_right_begin : S_len - 1 - s_left_begin, sl = right ? s_right_len : s_left_begin + 1;
     const int t0 = right ? t_right_begin : T_len - 1 - t_left_begin, tl = right ? t_right_len : t_left_begin + 1;
-    warp_dp(swap ? tw : sw, swap ? t0 : s0, swap ? tl : sl, swap ? sw : tw, swap ? s0 : t0, swap ? sl : tl,
+    warp_dp<ILP>(swap ? tw : sw, swap ? t0 : s0, swap ? tl : sl, swap ? sw : tw, swap ? s0 : t0, swap ? sl : tl,
             right ? error_limit : error_limit - right_errors, right, err_flags, lane);
     const DpOut o = C.o;
     const int s_end = swap ? o.t_end : o.a_end, t_end = swap ? o.a_end : o.t_end;
@@ -593,7 +646,7 @@ __device__ __forceinline__ void bind_warp_ctl(const DevParams &P, const ExtScrat
     C.gring1 = C.gring0 + X.gring_cap;
     C.arena = X.arena + (size_t)gwarp * X.arena_cap;  C.arena_cap = X.arena_cap;
     const size_t st = (size_t)X.emax + 2;
-    C.row_left = X.row_left + gwarp * st;  C.row_off = X.row_off + gwarp * st;
+    C.row_meta = X.row_meta + gwarp * st;
     C.path = X.path + gwarp * st;  C.ival = X.ival + gwarp * st;  C.ikc = X.ikc + gwarp * st;
     C.ldelta = X.ldelta + gwarp * st;  C.rdelta = X.rdelta + gwarp * st;
     C.emax = X.emax;
@@ -604,7 +657,7 @@ __device__ __forceinline__ void bind_warp_ctl(const DevParams &P, const ExtScrat
 }
 
 //  Persistent kernel: warps pull pairs from a global cursor (pairs differ wildly in cost).
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, int ILP>
 __global__ void __launch_bounds__(EXT_THREADS, MIN_BLOCKS)
 k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, const uint32_t *__restrict__ order, uint64_t n_pairs,
                const int32_t *__restrict__ seed_start, const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_len,
@@ -664,7 +717,7 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, co
       const int m_start = seed_start[sb + li], m_offset = seed_off[sb + li], m_len = seed_len[sb + li];
 
       int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
-      const int kind = warp_extend_alignment(m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len, err_flags, lane);
+      const int kind = warp_extend_alignment<ILP>(m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len, err_flags, lane);
 
       const bool usable = (kind == OVL_DOVETAIL) || P.partial;
       if (lane == 0 && usable && 1 + s_hi - s_lo >= P.min_olap_len && 1 + t_hi - t_lo >= P.min_olap_len) {
@@ -770,7 +823,7 @@ k_debug_extend(DevParams P_, ExtScratch X, uint32_t n, const uint32_t *__restric
     }
     __syncwarp();
     int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
-    int kind = warp_extend_alignment(m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
+    int kind = warp_extend_alignment<2>(m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
                                      &counters[CT_ERR_FLAGS], lane);
     if (lane == 0) {
       int32_t *o = out7 + 7 * i;
@@ -793,7 +846,7 @@ k_debug_extend(DevParams P_, ExtScratch X, uint32_t n, const uint32_t *__restric
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ovl_set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return OVLB_ERR_CUDA; } } while (0)
 
 static void free_ext(ExtScratch &X) {
-  void *ptrs[] = { X.arena, X.row_left, X.row_off, X.gring, X.path, X.ival, X.ikc, X.ldelta, X.rdelta };
+  void *ptrs[] = { X.arena, X.row_meta, X.gring, X.path, X.ival, X.ikc, X.ldelta, X.rdelta };
   for (void *p : ptrs) if (p) cudaFree(p);
   X = ExtScratch();
 }
@@ -823,9 +876,8 @@ int ovl_prepare_ext_scratch(ovlb_ctx *c) {
   X.n_warps = want_warps;
   const size_t st = (size_t)emax + 2;
   CK(cudaMalloc((void **)&X.arena, (size_t)want_warps * X.arena_cap * sizeof(uint2)));
-  CK(cudaMalloc((void **)&X.gring, (size_t)want_warps * 2 * gcap * 4));
-  CK(cudaMalloc((void **)&X.row_left, want_warps * st * 4));
-  CK(cudaMalloc((void **)&X.row_off, want_warps * st * 4));
+  CK(cudaMalloc((void **)&X.gring, ((size_t)want_warps * 2 * gcap + SRING_PAD) * 4));   // + slack: masked lanes read past the last ring
+  CK(cudaMalloc((void **)&X.row_meta, want_warps * st * 8));
   CK(cudaMalloc((void **)&X.path, want_warps * st));
   CK(cudaMalloc((void **)&X.ival, want_warps * st * 4));
   CK(cudaMalloc((void **)&X.ikc, want_warps * st * 4));
@@ -833,9 +885,10 @@ int ovl_prepare_ext_scratch(ovlb_ctx *c) {
   CK(cudaMalloc((void **)&X.rdelta, want_warps * st * 4));
   c->ext = X;
   const int smem = EXT_SM_BYTES;
-  CK(cudaFuncSetAttribute(k_extend_pairs<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(k_extend_pairs<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CK(cudaFuncSetAttribute(k_extend_pairs<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((k_extend_pairs<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((k_extend_pairs<4, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((k_extend_pairs<3, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute((k_extend_pairs<4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_debug_extend, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   return OVLB_OK;
 }
@@ -856,14 +909,20 @@ int ovl_extend_pairs(ovlb_ctx *c) {
   int blocks = c->ext.n_warps / EXT_WARPS;
   uint64_t need_blocks = (c->n_pairs + EXT_WARPS - 1) / EXT_WARPS;
   if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
-  static const int min_blocks = [] { const char *ev = getenv("OVLB_EXT_BLOCKS"); const int v = ev ? atoi(ev) : 4; return (v < 2 || v > 4) ? 4 : v; }();
+  static const int min_blocks = [] { const char *ev = getenv("OVLB_EXT_BLOCKS"); const int v = ev ? atoi(ev) : 4; return (v < 3 || v > 4) ? 4 : v; }();
+  //  two 32-cell groups in flight per iteration pay on wide bands (noisy reads: +2 % at --maxerate 0.06) and cost on
+  //  HiFi-like reads, whose rows are 3-25 cells wide (14.5 -> 16.2 ms per C2 tile): chosen by the seeds-per-pair ratio
+  //  that also selects the heaviest-first pair order
+  static const int ilp_env = [] { const char *ev = getenv("OVLB_EXT_ILP"); return ev ? atoi(ev) : 0; }();
+  const int ilp = ilp_env ? (ilp_env == 1 ? 1 : 2) : (c->pair_order ? 2 : 1);
   if ((uint64_t)c->sm_count * min_blocks < (uint64_t)blocks) blocks = c->sm_count * min_blocks;
-#define EXT_LAUNCH(MB) k_extend_pairs<MB><<<blocks, EXT_THREADS, smem, c->stream>>>( \
+#define EXT_LAUNCH(MB, IL) k_extend_pairs<MB, IL><<<blocks, EXT_THREADS, smem, c->stream>>>( \
       c->dp, c->ext, c->pairs, c->pair_order, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \
       c->ref.fwd, c->ref.rc, c->ref.woff, c->ref.len, c->ref.first_id, \
       c->hash.fwd, c->hash.rc, c->hash.woff, c->hash.len, c->hash.first_id, \
       c->d_records, c->rec_cap, c->d_work, c->d_counters->v)
-  if (min_blocks == 2) EXT_LAUNCH(2); else if (min_blocks == 4) EXT_LAUNCH(4); else EXT_LAUNCH(3);
+  if (min_blocks == 4) { if (ilp == 2) EXT_LAUNCH(4, 2); else EXT_LAUNCH(4, 1); }
+  else                 { if (ilp == 2) EXT_LAUNCH(3, 2); else EXT_LAUNCH(3, 1); }
 #undef EXT_LAUNCH
   c->launches++;
   c->ext_warps_launched = (uint64_t)blocks * EXT_WARPS;
