@@ -131,6 +131,24 @@ int main(int argc, char **argv) {
     printf("first %zu second %zu only-first %zu only-second %zu\n", A.size(), B.size(), onlyA, onlyB);
     return (onlyA || onlyB) ? 1 : 0;
   }
-  fprintf(stderr, "usage: ovltool dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
+  if (argc >= 3 && !strcmp(argv[1], "lengths")) {                      // read lengths as the overlapper sees them, one per line (ID order)
+    SqStore S;
+    if (!S.open(argv[2], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    for (uint32_t id = 1; id <= S.lastReadID(); id++) printf("%u\n", S.readLength(id));
+    return 0;
+  }
+  if (argc >= 3 && !strcmp(argv[1], "hash-ovb")) {                     // order-independent digest of a (large) .ovb: count + 2 x 64-bit sums of per-record hashes
+    std::vector<ovlb_record> recs;
+    if (!read_ovb(argv[2], recs, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    uint64_t s1 = 0, s2 = 0;
+    auto mix = [](uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33; return x; };
+    for (auto &r : recs) {
+      const uint64_t h = mix(mix(((uint64_t)r.a_iid << 32) | r.b_iid) ^ mix(r.dat0 + 0x9E3779B97F4A7C15ull) ^ mix(r.dat1 * 3 + 1));
+      s1 += h; s2 += mix(h);
+    }
+    printf("%zu:%016lx%016lx\n", recs.size(), (unsigned long)s1, (unsigned long)s2);
+    return 0;
+  }
+  fprintf(stderr, "usage: ovltool lengths <seqStore> | hash-ovb <file.ovb> | dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
   return 1;
 }
