@@ -911,10 +911,9 @@ int ovl_extend_pairs(ovlb_ctx *c) {
   if ((uint64_t)blocks > need_blocks) blocks = (int)need_blocks;
   static const int min_blocks = [] { const char *ev = getenv("OVLB_EXT_BLOCKS"); const int v = ev ? atoi(ev) : 4; return (v < 3 || v > 4) ? 4 : v; }();
   //  two 32-cell groups in flight per iteration pay on wide bands (noisy reads: +2 % at --maxerate 0.06) and cost on
-  //  HiFi-like reads, whose rows are 3-25 cells wide (14.5 -> 16.2 ms per C2 tile): chosen by the seeds-per-pair ratio
-  //  that also selects the heaviest-first pair order
+  //  HiFi-like reads, whose rows are 3-25 cells wide (14.5 -> 16.2 ms per C2 tile): chosen by the error rate of the job
   static const int ilp_env = [] { const char *ev = getenv("OVLB_EXT_ILP"); return ev ? atoi(ev) : 0; }();
-  const int ilp = ilp_env ? (ilp_env == 1 ? 1 : 2) : (c->pair_order ? 2 : 1);
+  const int ilp = ilp_env ? (ilp_env == 1 ? 1 : 2) : (c->P.max_erate >= 0.025 ? 2 : 1);
   if ((uint64_t)c->sm_count * min_blocks < (uint64_t)blocks) blocks = c->sm_count * min_blocks;
 #define EXT_LAUNCH(MB, IL) k_extend_pairs<MB, IL><<<blocks, EXT_THREADS, smem, c->stream>>>( \
       c->dp, c->ext, c->pairs, c->pair_order, c->n_pairs, c->seed_start, c->seed_off, c->seed_len, c->seed_alive, \

@@ -117,13 +117,25 @@ k_fill_groups(const uint64_t *__restrict__ pbase, uint32_t *__restrict__ grp_rea
 //  end of the read or holds a base that is not ACGT.  `cls` is the class of the PRECEDING base:
 //  0 = none (start of read, or N), 1..4 = A,C,G,T.
 // ------------------------------------------------------------------------------------------------
+//  the word lane `lane` (< 5) contributes to the k-mers of group p0: split from the arithmetic so that a caller can have
+//  the loads of many groups in flight at once
+__device__ __forceinline__ uint64_t warp_kmers_load(const uint64_t *__restrict__ w, int p0, int lane, bool &have) {
+  const int idx = (p0 >> 4) - 1 + lane;
+  have = lane < 5 && idx >= 0;
+  return have ? w[idx] : 0ull;
+}
+__device__ __forceinline__ bool warp_kmers_from(uint64_t word, bool have, int p0, int L, int K, int lane, uint64_t &key, int &cls);
+
 __device__ __forceinline__ bool warp_kmers(const uint64_t *__restrict__ w, int p0, int L, int K, int lane,
                                            uint64_t &key, int &cls) {
+  bool have;
+  const uint64_t word = warp_kmers_load(w, p0, lane, have);
+  return warp_kmers_from(word, have, p0, L, K, lane, key, cls);
+}
+
+__device__ __forceinline__ bool warp_kmers_from(uint64_t word, bool have, int p0, int L, int K, int lane, uint64_t &key, int &cls) {
   uint32_t codes = 0, inv = 0xFFFFu;
-  if (lane < 5) {
-    const int idx = (p0 >> 4) - 1 + lane;
-    if (idx >= 0) codes = ovl_codes16(w[idx], &inv);
-  }
+  if (have) codes = ovl_codes16(word, &inv);
   const int j0 = 1 + (lane >> 4);                      // first of my three words (word 0 = the one before p0)
   const uint32_t cp = __shfl_sync(0xffffffffu, codes, j0 - 1), ip = __shfl_sync(0xffffffffu, inv, j0 - 1);
   const uint32_t c0 = __shfl_sync(0xffffffffu, codes, j0),     i0 = __shfl_sync(0xffffffffu, inv, j0);
@@ -202,197 +214,23 @@ k_hash_tuples(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ wof
   tval[g * 32 + lane] = (uint32_t)(g * 32 + lane);
 }
 
-//  Tuples for the bucketed build: only the valid windows, compacted (one atomic per block), and the k-mer replaced
-//  by k-mer * mixc mod 4^K -- a bijection whose TOP bits depend on every base, so that the top bits of the key cut the
-//  tuples into even buckets whatever the base composition of the reads.
-__global__ void __launch_bounds__(THREADS)
-k_hash_tuples_compact(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
-                      const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read, uint64_t n_groups,
-                      int K, uint64_t mixc, uint64_t *__restrict__ tkey, uint32_t *__restrict__ tval, unsigned long long *counter) {
-  __shared__ unsigned int wcnt[WARPS_PER_BLOCK];
-  __shared__ unsigned long long blk_base;
-  const uint64_t g = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint64_t key = 0; int cls = 0; bool ok = false;
-  if (g < n_groups) {
-    const uint32_t r = grp_read[g];
-    ok = warp_kmers(fwd + woff[r], (int)(g * 32 - pbase[r]), (int)len[r], K, lane, key, cls);
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, ok);
-  if (lane == 0) wcnt[wid] = __popc(m);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int tot = 0;
-    #pragma unroll
-    for (int w = 0; w < WARPS_PER_BLOCK; w++) { const unsigned int t = wcnt[w]; wcnt[w] = tot; tot += t; }
-    blk_base = tot ? atomicAdd(counter, (unsigned long long)tot) : 0ull;
-  }
-  __syncthreads();
-  if (ok) {
-    const uint64_t i = blk_base + wcnt[wid] + __popc(m & ((1u << lane) - 1));
-    tkey[i] = (((key * mixc) & ((1ull << (2 * K)) - 1)) << 3) | (uint64_t)cls;
-    tval[i] = (uint32_t)(g * 32 + lane);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-//  Bucketed index build.  After ceil(B/8) radix passes over the top B bits of the (mixed) tuple keys the tuples of a
-//  bucket are contiguous (a few thousand: BK_TARGET on average).  One CTA then finishes a bucket entirely in shared
-//  memory: a hash table gives every distinct k-mer of the bucket a slot and counts its occurrences per class of the
-//  preceding base, a prefix sum turns the counts into offsets, and the positions are scattered to their
-//  (k-mer, class) segment.  That is everything the index needs -- the order of the k-mers inside a bucket and of the
-//  positions inside a class is immaterial -- so the remaining radix passes, the distinct count and the
-//  class-boundary searches of the sorted build (k_count_distinct, k_group_heads) are not run at all.
+//  Bucketed index build.  The tuples (mixed k-mer << 3 | class, position) are cut into buckets of ~BK_TARGET by the top
+//  B bits of the key (two partition kernels below); one CTA then finishes a bucket entirely in shared memory: a hash
+//  table gives every distinct k-mer of the bucket a slot and counts its occurrences per class of the preceding base, a
+//  prefix sum turns the counts into offsets, and the positions are scattered to their (k-mer, class) segment.  That is
+//  everything the index needs -- the order of the k-mers inside a bucket and of the positions inside a class is
+//  immaterial -- so no sort, no distinct count and no class-boundary searches (k_count_distinct, k_group_heads of the
+//  sorted build) are run at all.  Two CTAs of 512 threads share an SM (109 KB of shared memory each): one CTA's
+//  barrier-separated phases overlap the other's.
 // ------------------------------------------------------------------------------------------------
-#define BK_THREADS 1024
+#define BK_THREADS 512
+#define BK_CAP     3072                 // tuples of a bucket that fit shared memory
 #define BK_PER     (BK_CAP / BK_THREADS)     // tuples per thread, staged in registers
-#define BK_CAP     6144                 // tuples of a bucket that fit shared memory
-#define BK_TARGET  4096                 // mean bucket size the bucket count is chosen for
-#define BK_TABLE   4096                 // hash-table entries per bucket
-#define BK_MAXDIST 3584                 // distinct k-mers a bucket may hold (load 0.875)
-#define BK_SMEM    (BK_TABLE * 8 + BK_CAP * 4 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
-
-//  first tuple of every bucket (bucket = key >> shift) in the partitioned tuple array; offs[nb] = n
-__global__ void k_bucket_offsets(const uint64_t *__restrict__ key, uint64_t n, int shift, uint32_t nb, uint32_t *__restrict__ offs) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > nb) return;
-  if (b == nb) { offs[b] = (uint32_t)n; return; }
-  uint64_t lo = 0, hi = n;
-  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((key[mid] >> shift) < b) lo = mid + 1; else hi = mid; }
-  offs[b] = (uint32_t)lo;
-}
-
-//  out[0]: distinct k-mers (slot records emitted), out[1]: bit 0 = a bucket did not fit (caller falls back to the
-//  sorted build)
-__global__ void __launch_bounds__(BK_THREADS, 1)
-k_bucket_group(const uint64_t *__restrict__ pkey, const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ offs, uint32_t nb,
-               int K, uint64_t mix_inv, uint32_t *__restrict__ occ, IndexSlot *__restrict__ tmp, uint32_t tmp_cap,
-               uint32_t *__restrict__ gk, uint32_t *__restrict__ gv, unsigned long long *out) {
-  extern __shared__ __align__(16) unsigned char bk_sm[];
-  uint64_t *hk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_TABLE] mixed k-mer of the slot
-  uint32_t *gpos = reinterpret_cast<uint32_t *>(hk + BK_TABLE);          // [BK_CAP] positions grouped by (slot, class)
-  uint32_t *tp = gpos + BK_CAP;                                          // [BK_CAP] position of each tuple (keys stay in registers)
-  uint16_t *ts = reinterpret_cast<uint16_t *>(tp + BK_CAP);              // [BK_CAP] slot << 3 | class
-  uint32_t *hc = reinterpret_cast<uint32_t *>(ts + BK_CAP);              // [BK_TABLE * 5] count -> start -> end of (slot, class)
-  uint32_t *hm = hc + BK_TABLE * 5;                                      // [BK_TABLE] first (smallest) position of the slot's k-mer
-  __shared__ unsigned int n_dist, bad, slot_base;
-  __shared__ unsigned int wsum[BK_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint64_t kmask = (1ull << (2 * K)) - 1;
-
-  for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
-    const uint32_t s0 = offs[b], m = offs[b + 1] - s0;
-    if (m == 0) continue;
-    if (m > BK_CAP) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
-    __syncthreads();                                                     // previous bucket fully written out
-    for (int i = tid; i < BK_TABLE; i += BK_THREADS) { hk[i] = ~0ull; hm[i] = 0xFFFFFFFFu; }
-    for (int i = tid; i < BK_TABLE * 5; i += BK_THREADS) hc[i] = 0;
-    if (tid == 0) { n_dist = 0; bad = 0; }
-    __syncthreads();
-    //  load (all of a thread's tuples in flight at once), find/insert the k-mer, count per (slot, class)
-    uint64_t kreg[BK_PER]; uint32_t preg[BK_PER];
-    #pragma unroll
-    for (int j = 0; j < BK_PER; j++) {
-      const uint32_t i = tid + j * BK_THREADS;
-      kreg[j] = i < m ? pkey[s0 + i] : 0ull;
-      preg[j] = i < m ? ppos[s0 + i] : 0u;
-    }
-    #pragma unroll
-    for (int j = 0; j < BK_PER; j++) {
-      const uint32_t i = tid + j * BK_THREADS;
-      if (i >= m) break;
-      const uint64_t t = kreg[j];
-      tp[i] = preg[j];
-      const uint32_t cls = (uint32_t)t & 7u;
-      const uint64_t km = t >> 3;
-      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> 52);      // 12 bits
-      while (true) {
-        const uint64_t cur = hk[h];
-        if (cur == km) break;
-        if (cur == ~0ull) {
-          const unsigned long long old = atomicCAS((unsigned long long *)&hk[h], ~0ull, (unsigned long long)km);
-          if (old == ~0ull) { if (atomicAdd(&n_dist, 1u) >= BK_MAXDIST) bad = 1; break; }
-          if (old == km) break;
-        }
-        if (bad) break;
-        h = (h + 1) & (BK_TABLE - 1);
-      }
-      ts[i] = (uint16_t)((h << 3) | cls);
-      atomicAdd(&hc[h * 5 + cls], 1u);
-      atomicMin(&hm[h], preg[j]);
-    }
-    __syncthreads();
-    if (bad) { if (tid == 0) atomicOr(&out[1], 1ull); continue; }
-    //  exclusive prefix sum over hc[slot * 5 + class] in slot order: every thread owns 40 consecutive entries
-    {
-      const int per = BK_TABLE * 5 / BK_THREADS;
-      uint32_t sum = 0;
-      for (int j = 0; j < per; j++) sum += hc[tid * per + j];
-      uint32_t inc = sum;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-      if (lane == 31) wsum[wid] = inc;
-      __syncthreads();
-      if (wid == 0) {
-        uint32_t w = lane < BK_THREADS / 32 ? wsum[lane] : 0, wi = w;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
-        if (lane < BK_THREADS / 32) wsum[lane] = wi - w;
-      }
-      __syncthreads();
-      uint32_t run = wsum[wid] + inc - sum;
-      for (int j = 0; j < per; j++) { const uint32_t c = hc[tid * per + j]; hc[tid * per + j] = run; run += c; }
-    }
-    if (tid == 0) {
-      const unsigned int nd = n_dist;
-      const unsigned long long base = atomicAdd(&out[0], (unsigned long long)nd);
-      slot_base = (base + nd <= tmp_cap) ? (unsigned int)base : 0xFFFFFFFFu;
-      if (base + nd > tmp_cap) atomicOr(&out[1], 1ull);
-    }
-    __syncthreads();
-    //  scatter the positions to their segment: hc becomes the END of every (slot, class)
-    for (uint32_t i = tid; i < m; i += BK_THREADS) {
-      const uint32_t sc = ts[i];
-      const uint32_t dst = atomicAdd(&hc[(sc >> 3) * 5 + (sc & 7u)], 1u);
-      gpos[dst] = tp[i];
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < m; i += BK_THREADS) occ[s0 + i] = gpos[i];
-    //  one slot record per occupied table entry: every thread owns BK_TABLE / BK_THREADS consecutive entries
-    if (slot_base != 0xFFFFFFFFu) {
-      const int per = BK_TABLE / BK_THREADS;
-      uint32_t mine = 0;
-      #pragma unroll
-      for (int j = 0; j < per; j++) mine += hk[tid * per + j] != ~0ull;
-      uint32_t inc = mine;
-      #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-      if (lane == 31) wsum[wid] = inc;
-      __syncthreads();
-      if (wid == 0) {
-        uint32_t w = wsum[lane], wi = w;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
-        wsum[lane] = wi - w;
-      }
-      __syncthreads();
-      uint32_t c = slot_base + wsum[wid] + inc - mine;
-      #pragma unroll
-      for (int j = 0; j < per; j++) {
-        const int h = tid * per + j;
-        const uint64_t km = hk[h];
-        if (km == ~0ull) continue;
-        const uint32_t st = h ? hc[h * 5 - 1] : 0u;
-        const uint64_t kmer = (km * mix_inv) & kmask;
-        uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
-        sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), s0 + st, s0 + hc[h * 5]);
-        sp[1] = make_uint4(s0 + hc[h * 5 + 1], s0 + hc[h * 5 + 2], s0 + hc[h * 5 + 3], s0 + hc[h * 5 + 4]);
-        gk[c] = hm[h]; gv[c] = c;
-        c++;
-      }
-    }
-  }
-}
+#define BK_TARGET  2048                 // mean bucket size the bucket count is chosen for
+#define BK_TABLE_BITS 11
+#define BK_TABLE   (1 << BK_TABLE_BITS) // hash-table entries per bucket
+#define BK_MAXDIST 1792                 // distinct k-mers a bucket may hold (load 0.875)
 
 //  counts distinct k-mers and finds the number of valid tuples in the sorted array
 #define CNT_PER_THREAD 8
@@ -542,6 +380,407 @@ k_path_slots(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ ord
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint4 *src = reinterpret_cast<const uint4 *>(&tmp[order[j]]);
+  const uint4 a = src[0], b = src[1];
+  uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
+  dst[0] = a; dst[1] = b;
+  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  Bucketed build, round 2: no library sort on the way.
+//
+//    k_part1        k-mers of a 4096-position chunk -> tuples, scattered straight into 2^B1 coarse partitions of the top B1
+//                   bits of the mixed key (fixed-stride regions, one global reservation per (chunk, partition)); the
+//                   12-byte tuple is written once, already partitioned -- no separate tuple array, no first sort pass
+//    k_part2        a 4096-tuple chunk of one coarse partition -> 2^B2 buckets; the tuple shrinks to 8 bytes on the way:
+//                   the top B bits are the bucket number, what is left of the key shares a word with the position
+//    k_bucket_group2  one bucket per CTA iteration; the bucket's tuples arrive in shared memory by ONE bulk asynchronous
+//                   copy (cp.async.bulk + mbarrier: the TMA unit moves them, no thread issues loads), and the copy of
+//                   the NEXT bucket is in flight while this one is grouped
+//    path order     = rank of the k-mer's first position among all first positions: a bitmap of first positions
+//                   (31 MB per 250 M positions, L2 resident), a prefix popcount, and every distinct k-mer computes its
+//                   own slot index -- no sort of (position, slot) pairs
+//
+//  Bytes per hash k-mer (K <= 24): 0.5 read + 12 written (part1), 12 read + 8 written (part2), 8 read + 4 written
+//  (bucket_group2) = 44.5, against 72.5 for tuples + two library radix passes + bucket read in round 1.
+// ------------------------------------------------------------------------------------------------
+#define PART_CH      4096               // tuples per CTA chunk of k_part2
+#define PART_THREADS 256
+#define PART_MAXD    1024               // digits per level (B1, B2 <= 10)
+#define CNT1_STRIDE  32                 // u32 words between two coarse-partition cursors: one 128-byte line each
+#define PART1_GROUPS 256                // 32-position groups per CTA of k_part1: one group per THREAD
+
+//  k_part1: one THREAD per 32-position group.  The thread loads the five dp4 words that hold the group's windows itself,
+//  converts them to 2-bit codes once and then walks the 32 windows in registers (shift, mask, multiply): no shuffles,
+//  no staging in shared memory.  (A first version computed the k-mers warp-wide with shuffles and staged tuples and
+//  ranks in shared memory: 19 shared-memory / shuffle / scattered-store operations per 32 tuples against 3 in k_part2,
+//  and ncu showed it MIO-bound -- `mio` and `short_scoreboard` stalls, 14.7 % issue active, 9.5 ms.)  Two passes over
+//  the windows: count per partition (shared-memory histogram), reserve the CTA's share of every partition with one
+//  global atomic per partition, then recompute, take a slot and write the 16-byte tuple record in place.
+__device__ __forceinline__ bool group_window(uint64_t lo, uint64_t hi, uint64_t iv, uint32_t prev_code0, uint32_t prev_inv0,
+                                             int w, int p0, int L, int K, uint64_t kmask, uint64_t &key, int &cls) {
+  const int sh = 2 * w;
+  key = (w ? ((lo >> sh) | (hi << (64 - sh))) : lo) & kmask;
+  const uint32_t bad = (uint32_t)(iv >> w) & ((1u << K) - 1u);          // K <= 30
+  uint32_t pc, pi;
+  if (w) { const int b = w - 1; pc = (uint32_t)(lo >> (2 * b)) & 3u; pi = (uint32_t)(iv >> b) & 1u; }
+  else   { pc = prev_code0; pi = prev_inv0; }
+  const int p = p0 + w;
+  cls = (p > 0 && pi == 0) ? (int)(1 + pc) : 0;
+  return (p + K <= L) && bad == 0;
+}
+
+__global__ void __launch_bounds__(PART_THREADS)
+k_part1(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
+        const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read, uint64_t n_groups,
+        int K, uint64_t mixc, int sh1, uint32_t nd1, uint64_t cap1,
+        uint4 *__restrict__ trec, unsigned int *cnt1, unsigned long long *flag) {
+  __shared__ uint32_t hist[PART_MAXD], cursor[PART_MAXD];
+  const int tid = threadIdx.x;
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  for (uint32_t d = tid; d < nd1; d += PART_THREADS) hist[d] = 0;
+  const uint64_t g = (uint64_t)blockIdx.x * PART1_GROUPS + tid;
+  uint64_t lo = 0, hi = 0, iv = ~0ull; uint32_t pc0 = 0, pi0 = 1; int p0 = 0, L = 0;
+  if (g < n_groups) {
+    const uint32_t r = grp_read[g];
+    const uint64_t *w = fwd + woff[r];
+    L = (int)len[r];
+    p0 = (int)(g * 32 - pbase[r]);
+    const int i0 = (p0 >> 4) - 1;                                        // word of the 16 bases before p0
+    uint64_t wd[5];
+    #pragma unroll
+    for (int j = 0; j < 5; j++) wd[j] = (i0 + j >= 0) ? w[i0 + j] : 0ull;   // reads end in two zero pad words: in bounds
+    uint32_t c[5], in[5];
+    #pragma unroll
+    for (int j = 0; j < 5; j++) c[j] = ovl_codes16(wd[j], &in[j]);
+    lo = (uint64_t)c[1] | ((uint64_t)c[2] << 32); hi = (uint64_t)c[3] | ((uint64_t)c[4] << 32);
+    iv = (uint64_t)in[1] | ((uint64_t)in[2] << 16) | ((uint64_t)in[3] << 32) | ((uint64_t)in[4] << 48);
+    pc0 = c[0] >> 30; pi0 = (i0 >= 0) ? (in[0] >> 15) : 1u;
+  }
+  __syncthreads();
+  for (int w = 0; w < 32; w++) {
+    uint64_t key; int cls;
+    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls)) {
+      const uint64_t t = (((key * mixc) & kmask) << 3) | (uint64_t)cls;
+      atomicAdd(&hist[(uint32_t)(t >> sh1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (uint32_t d = tid; d < nd1; d += PART_THREADS) { const uint32_t h = hist[d]; cursor[d] = h ? atomicAdd(&cnt1[d * CNT1_STRIDE], h) : 0u; }
+  __syncthreads();
+  bool over = false;
+  for (int w = 0; w < 32; w++) {
+    uint64_t key; int cls;
+    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls)) {
+      const uint64_t t = (((key * mixc) & kmask) << 3) | (uint64_t)cls;
+      const uint32_t d = (uint32_t)(t >> sh1);
+      const uint64_t o = atomicAdd(&cursor[d], 1u);
+      if (o < cap1) trec[d * cap1 + o] = make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)(g * 32 + w), 0u);
+      else over = true;
+    }
+  }
+  if (over) atomicOr(flag, 1ull);
+}
+
+#define PART2_THREADS 512
+#define PART2_PER     (PART_CH / PART2_THREADS)
+__global__ void __launch_bounds__(PART2_THREADS)
+k_part2(const uint4 *__restrict__ trec, const unsigned int *__restrict__ cnt1, uint64_t cap1,
+        int sh2, int B2, uint64_t lowmask, int posbits, uint32_t bk_cap,
+        uint64_t *__restrict__ btup, unsigned int *cnt2, unsigned long long *flag) {
+  __shared__ uint32_t hist[PART_MAXD], gbase[PART_MAXD];
+  const int tid = threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  const uint64_t n_in = min((uint64_t)cnt1[p * CNT1_STRIDE], cap1);
+  const uint64_t start = (uint64_t)blockIdx.x * PART_CH;
+  if (start >= n_in) return;
+  const uint32_t m = (uint32_t)min((uint64_t)PART_CH, n_in - start);
+  const uint32_t nd2 = 1u << B2;
+  for (uint32_t d = tid; d < nd2; d += PART2_THREADS) hist[d] = 0;
+  __syncthreads();
+  uint64_t t[PART2_PER]; uint32_t pos[PART2_PER], rk[PART2_PER];
+  const uint4 *src = trec + (uint64_t)p * cap1 + start;
+  #pragma unroll
+  for (int i = 0; i < PART2_PER; i++) {
+    const uint32_t j = tid + i * PART2_THREADS;
+    const uint4 v = j < m ? src[j] : make_uint4(0, 0, 0, 0);
+    t[i] = (uint64_t)v.x | ((uint64_t)v.y << 32);
+    pos[i] = v.z;
+  }
+  #pragma unroll
+  for (int i = 0; i < PART2_PER; i++) {
+    const uint32_t j = tid + i * PART2_THREADS;
+    if (j < m) rk[i] = atomicAdd(&hist[(uint32_t)(t[i] >> sh2) & (nd2 - 1)], 1u);
+  }
+  __syncthreads();
+  for (uint32_t d = tid; d < nd2; d += PART2_THREADS) { const uint32_t h = hist[d]; gbase[d] = h ? atomicAdd(&cnt2[(p << B2) + d], h) : 0u; }
+  __syncthreads();
+  bool over = false;
+  #pragma unroll
+  for (int i = 0; i < PART2_PER; i++) {
+    const uint32_t j = tid + i * PART2_THREADS;
+    if (j >= m) continue;
+    const uint32_t d = (uint32_t)(t[i] >> sh2) & (nd2 - 1);
+    const uint32_t o = gbase[d] + rk[i];
+    if (o < bk_cap) btup[(uint64_t)((p << B2) + d) * bk_cap + o] = ((t[i] & lowmask) << posbits) | pos[i];
+    else over = true;
+  }
+  if (over) atomicOr(flag, 1ull);
+}
+
+//  exclusive prefix sum of min(cnt, cap) over nb buckets, one CTA; offs[nb] = total
+__global__ void __launch_bounds__(1024)
+k_bucket_scan(const unsigned int *__restrict__ cnt, uint32_t nb, uint32_t cap, uint32_t *__restrict__ offs) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t i = base + tid;
+    const uint32_t v = i < nb ? min(cnt[i], cap) : 0u;
+    uint32_t inc = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = wsum[lane], wi = w;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+      wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    const uint32_t c0 = carry;
+    if (i < nb) offs[i] = c0 + wsum[wid] + inc - v;
+    __syncthreads();
+    if (tid == 1023) carry = c0 + wsum[wid] + inc;
+    __syncthreads();
+  }
+  if (tid == 0) offs[nb] = carry;
+}
+
+//  ---- bulk asynchronous copy + mbarrier (sm_90+; SASS: UBLKCP.S.G, SYNCS.*) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+//  one thread: expect `bytes`, then start the copy global -> shared; completion flips the barrier's phase
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+#define BK2_SMEM (BK_TABLE * 8 + BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
+
+//  out[0]: distinct k-mers (slot records emitted), out[1]: bit 0 = a bucket did not fit
+__global__ void __launch_bounds__(BK_THREADS, 2)
+k_bucket_group2(const uint64_t *__restrict__ btup, const unsigned int *__restrict__ cnt2, const uint32_t *__restrict__ offs, uint32_t nb,
+                int K, int B, int posbits, uint64_t mix_inv, uint32_t *__restrict__ occ, IndexSlot *__restrict__ tmp, uint32_t tmp_cap,
+                uint32_t *__restrict__ first_pos, uint32_t *first_bitmap, unsigned long long *out) {
+  extern __shared__ __align__(128) unsigned char bk_sm[];
+  uint64_t *hk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_TABLE] low key bits (mixed k-mer below the bucket bits) of the slot
+  uint64_t *tbuf = hk + BK_TABLE;                                        // [BK_CAP] the bucket's tuples, filled by the bulk copy
+  uint32_t *gpos = reinterpret_cast<uint32_t *>(tbuf + BK_CAP);          // [BK_CAP] positions grouped by (slot, class)
+  uint16_t *ts = reinterpret_cast<uint16_t *>(gpos + BK_CAP);            // [BK_CAP] slot << 3 | class
+  uint32_t *hc = reinterpret_cast<uint32_t *>(ts + BK_CAP);              // [BK_TABLE * 5] count -> start -> end of (slot, class)
+  uint32_t *hm = hc + BK_TABLE * 5;                                      // [BK_TABLE] first (smallest) position of the slot's k-mer
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned int n_dist, bad, slot_base;
+  __shared__ unsigned int wsum[BK_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  const uint64_t posmask = (1ull << posbits) - 1;
+  const int lowk = 2 * K - B;                                            // mixed k-mer bits below the bucket number
+
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t b = blockIdx.x;
+  while (b < nb && cnt2[b] == 0) b += gridDim.x;
+  if (tid == 0 && b < nb) bulk_load(tbuf, btup + (uint64_t)b * BK_CAP, ((min(cnt2[b], (unsigned)BK_CAP) * 8u + 15u) & ~15u), &bar);
+  uint32_t parity = 0;
+
+  while (b < nb) {
+    const uint32_t m = cnt2[b];
+    uint32_t nxt = b + gridDim.x;
+    while (nxt < nb && cnt2[nxt] == 0) nxt += gridDim.x;
+    if (m > BK_CAP) {                                                    // cannot happen after a clean k_part2 (it flags the overflow itself)
+      if (tid == 0) atomicOr(&out[1], 1ull);
+    }
+    const uint32_t s0 = offs[b];
+    for (int i = tid; i < BK_TABLE; i += BK_THREADS) { hk[i] = ~0ull; hm[i] = 0xFFFFFFFFu; }
+    for (int i = tid; i < BK_TABLE * 5; i += BK_THREADS) hc[i] = 0;
+    if (tid == 0) { n_dist = 0; bad = 0; }
+    mbar_wait(&bar, parity); parity ^= 1;                                // the bucket's tuples have landed
+    uint64_t kreg[BK_PER];
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      kreg[j] = i < m ? tbuf[i] : 0ull;
+    }
+    __syncthreads();                                                     // tbuf consumed, tables cleared
+    if (tid == 0 && nxt < nb) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy reads of tbuf before the async-proxy overwrite
+      bulk_load(tbuf, btup + (uint64_t)nxt * BK_CAP, ((min(cnt2[nxt], (unsigned)BK_CAP) * 8u + 15u) & ~15u), &bar);
+    }
+    //  find/insert the k-mer, count per (slot, class)
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      if (i >= m) break;
+      const uint64_t low = kreg[j] >> posbits;
+      const uint32_t pos = (uint32_t)(kreg[j] & posmask);
+      const uint32_t cls = (uint32_t)low & 7u;
+      const uint64_t km = low >> 3;
+      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> (64 - BK_TABLE_BITS));
+      while (true) {
+        const uint64_t cur = hk[h];
+        if (cur == km) break;
+        if (cur == ~0ull) {
+          const unsigned long long old = atomicCAS((unsigned long long *)&hk[h], ~0ull, (unsigned long long)km);
+          if (old == ~0ull) { if (atomicAdd(&n_dist, 1u) >= BK_MAXDIST) bad = 1; break; }
+          if (old == km) break;
+        }
+        if (bad) break;
+        h = (h + 1) & (BK_TABLE - 1);
+      }
+      ts[i] = (uint16_t)((h << 3) | cls);
+      atomicAdd(&hc[h * 5 + cls], 1u);
+      atomicMin(&hm[h], pos);
+    }
+    __syncthreads();
+    if (bad) { if (tid == 0) atomicOr(&out[1], 1ull); b = nxt; continue; }
+    //  exclusive prefix sum over hc[slot * 5 + class] in slot order: every thread owns 20 consecutive entries
+    {
+      const int per = BK_TABLE * 5 / BK_THREADS;
+      uint32_t sum = 0;
+      for (int j = 0; j < per; j++) sum += hc[tid * per + j];
+      uint32_t inc = sum;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        uint32_t w = lane < BK_THREADS / 32 ? wsum[lane] : 0, wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+        if (lane < BK_THREADS / 32) wsum[lane] = wi - w;
+      }
+      __syncthreads();
+      uint32_t run = wsum[wid] + inc - sum;
+      for (int j = 0; j < per; j++) { const uint32_t c = hc[tid * per + j]; hc[tid * per + j] = run; run += c; }
+    }
+    if (tid == 0) {
+      const unsigned int nd = n_dist;
+      const unsigned long long base = atomicAdd(&out[0], (unsigned long long)nd);
+      slot_base = (base + nd <= tmp_cap) ? (unsigned int)base : 0xFFFFFFFFu;
+      if (base + nd > tmp_cap) atomicOr(&out[1], 1ull);
+    }
+    __syncthreads();
+    //  scatter the positions to their segment: hc becomes the END of every (slot, class)
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      if (i >= m) break;
+      const uint32_t sc = ts[i];
+      const uint32_t dst = atomicAdd(&hc[(sc >> 3) * 5 + (sc & 7u)], 1u);
+      gpos[dst] = (uint32_t)(kreg[j] & posmask);
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += BK_THREADS) occ[s0 + i] = gpos[i];
+    //  one slot record per occupied table entry: every thread owns BK_TABLE / BK_THREADS consecutive entries
+    if (slot_base != 0xFFFFFFFFu) {
+      const int per = BK_TABLE / BK_THREADS;
+      uint32_t mine = 0;
+      #pragma unroll
+      for (int j = 0; j < per; j++) mine += hk[tid * per + j] != ~0ull;
+      uint32_t inc = mine;
+      #pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      if (wid == 0) {
+        uint32_t w = lane < BK_THREADS / 32 ? wsum[lane] : 0, wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += x; }
+        if (lane < BK_THREADS / 32) wsum[lane] = wi - w;
+      }
+      __syncthreads();
+      uint32_t c = slot_base + wsum[wid] + inc - mine;
+      #pragma unroll
+      for (int j = 0; j < per; j++) {
+        const int h = tid * per + j;
+        const uint64_t kl = hk[h];
+        if (kl == ~0ull) continue;
+        const uint32_t st = h ? hc[h * 5 - 1] : 0u;
+        const uint64_t km = ((uint64_t)b << lowk) | kl;                  // the mixed k-mer: bucket number on top
+        const uint64_t kmer = (km * mix_inv) & kmask;
+        uint4 *sp = reinterpret_cast<uint4 *>(&tmp[c]);
+        sp[0] = make_uint4((uint32_t)kmer, (uint32_t)(kmer >> 32), s0 + st, s0 + hc[h * 5]);
+        sp[1] = make_uint4(s0 + hc[h * 5 + 1], s0 + hc[h * 5 + 2], s0 + hc[h * 5 + 3], s0 + hc[h * 5 + 4]);
+        const uint32_t fp = hm[h];
+        first_pos[c] = fp;
+        atomicOr(&first_bitmap[fp >> 5], 1u << (fp & 31));
+        c++;
+      }
+    }
+    __syncthreads();                                                     // everyone is done with the tables before they are cleared again
+    b = nxt;
+  }
+}
+
+//  Path order without a sort: rank of a first position among all first positions = prefix popcount of the bitmap.
+//  wprefix[w] = number of set bits in words [0, w).  Three small kernels: per-block sums, scan of the sums, per-word prefix.
+#define BM_BLOCK 1024
+__global__ void __launch_bounds__(256)
+k_bm_blocksum(const uint32_t *__restrict__ bm, uint64_t n_words, uint32_t *__restrict__ bsum) {
+  __shared__ uint32_t ws[8];
+  const uint64_t base = (uint64_t)blockIdx.x * BM_BLOCK;
+  uint32_t s = 0;
+  for (int i = threadIdx.x; i < BM_BLOCK; i += 256) { const uint64_t w = base + i; if (w < n_words) s += __popc(bm[w]); }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; i++) t += ws[i]; bsum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256)
+k_bm_prefix(const uint32_t *__restrict__ bm, uint64_t n_words, const uint32_t *__restrict__ boff, uint32_t *__restrict__ wprefix) {
+  __shared__ uint32_t ws[8];
+  const uint64_t base = (uint64_t)blockIdx.x * BM_BLOCK;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  //  thread t owns words base + 4t .. base + 4t + 3
+  uint32_t c[4]; uint32_t s = 0;
+  #pragma unroll
+  for (int j = 0; j < 4; j++) { const uint64_t w = base + 4 * threadIdx.x + j; c[j] = w < n_words ? __popc(bm[w]) : 0; s += c[j]; }
+  uint32_t inc = s;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+  if (lane == 31) ws[wid] = inc;
+  __syncthreads();
+  uint32_t wb = 0;
+  for (int i = 0; i < wid; i++) wb += ws[i];
+  uint32_t run = boff[blockIdx.x] + wb + inc - s;
+  #pragma unroll
+  for (int j = 0; j < 4; j++) { const uint64_t w = base + 4 * threadIdx.x + j; if (w < n_words) wprefix[w] = run; run += c[j]; }
+}
+
+//  one thread per distinct k-mer: its path index from the bitmap, the slot written in place, the hash-table entry
+__global__ void __launch_bounds__(256)
+k_path_slots2(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ first_pos, uint32_t n,
+              const uint32_t *__restrict__ bm, const uint32_t *__restrict__ wprefix,
+              IndexSlot *__restrict__ slots, HashEntry *ht, uint64_t hcap) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const uint32_t fp = first_pos[c];
+  const uint32_t j = wprefix[fp >> 5] + __popc(bm[fp >> 5] & ((1u << (fp & 31)) - 1u));
+  const uint4 *src = reinterpret_cast<const uint4 *>(&tmp[c]);
   const uint4 a = src[0], b = src[1];
   uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
   dst[0] = a; dst[1] = b;
@@ -1158,10 +1397,6 @@ int ovl_build_index(ovlb_ctx *c) {
   const uint64_t sentinel = 1ull << (2 * K + 3);
 
   if ((rc = ensure_groups(c, H))) return rc;
-  if ((rc = ensure(X.tkey, X.tkey_cap, (size_t)n + 32))) return rc;
-  if ((rc = ensure(X.tkey2, X.tkey2_cap, (size_t)n + 32))) return rc;
-  if ((rc = ensure(X.tval, X.tval_cap, (size_t)n + 32))) return rc;
-  if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
 
   //  Bucketed build (default) or sorted build (OVLB_BUCKETED=0, or after a bucket overflowed)
   static const int bucketed_env = [] { const char *ev = getenv("OVLB_BUCKETED"); return ev ? atoi(ev) : 1; }();   // thread-safe init
@@ -1172,73 +1407,92 @@ int ovl_build_index(ovlb_ctx *c) {
   bool tmp_ready = false;
 
   for (int attempt = 0; attempt < 2; attempt++) {
-    //  (k-mer, class of the preceding base) -> position, one tuple per window
-    EvTimer t1(c->stream);
-    uint64_t nt = n;                                                      // tuples to partition / sort
-    if (n_groups && bucketed) {
-      CK(cudaMemsetAsync(&c->d_work[5], 0, 8, c->stream));
-      k_hash_tuples_compact<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K,
-                                                                                           mixc, X.tkey, X.tval, &c->d_work[5]);
-      unsigned long long nv = 0;
-      CK(cudaMemcpyAsync(&nv, &c->d_work[5], 8, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      nt = nv;
-      c->launches++;
-    } else if (n_groups) {
-      k_hash_tuples<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.tkey, X.tval);
-      c->launches++;
-    }
-    CK(cudaGetLastError());
-    c->timings.index_tuples_ms = t1.stop();
-    if (bucketed && nt < (1u << 16)) { bucketed = false; continue; }      // tiny block: the sorted build
+    if (bucketed && n < (1u << 16)) bucketed = false;                     // tiny block: the sorted build
+    //  bucket bits from the position count (an upper bound of the tuple count); the 8-byte bucket tuple needs the key
+    //  bits below the bucket number and the position to share 64 bits: 2K + 3 - B + posbits <= 64 (K <= 24 always fits)
+    int B = 2 * K + 3 < 8 ? 2 * K + 3 : 8; while (B < 2 * K && (n >> B) > BK_TARGET) B++;
+    int posbits = 1; while (posbits < 32 && (n >> posbits)) posbits++;
+    if (bucketed && (2 * K + 3 - B + posbits > 64 || B > 20 || B < 2)) bucketed = false;
+    const uint64_t tmp_cap = n / 4 * 3 + (1u << 20);
+    //  the bucketed build sizes its slot scratch for the worst case (3/4 of the tuples distinct) before it knows the
+    //  real count; if that does not fit a third of the memory budget use the sorted build, which counts first
+    if (bucketed && tmp_cap * (sizeof(IndexSlot) + 8) > c->mem_budget / 3) bucketed = false;
 
     if (bucketed) {
-      //  number of buckets: a power of two with ~BK_TARGET tuples each, cut out of the top bits of the 2K+3-bit key
-      int B = 2 * K + 3 < 8 ? 2 * K + 3 : 8; while (B < 2 * K && (nt >> B) > BK_TARGET) B++;
-      const uint32_t nb = 1u << B;
-      const int shift = 2 * K + 3 - B;
-      const uint64_t tmp_cap = nt / 4 * 3 + (1u << 20);
-      //  the bucketed build sizes its slot scratch for the worst case (3/4 of the tuples distinct) before it knows the
-      //  real count; if that does not fit a third of the memory budget use the sorted build, which counts first
-      if (tmp_cap * (sizeof(IndexSlot) + 8) > c->mem_budget / 3) { bucketed = false; attempt--; continue; }
+      const int B1 = (B + 1) / 2, B2 = B - B1;
+      const uint32_t nd1 = 1u << B1, nb = 1u << B;
+      const uint64_t mean1 = n >> B1;
+      uint64_t cap1 = mean1 + 16 * (uint64_t)sqrt((double)mean1) + PART_CH;
+      cap1 = (cap1 + 1) & ~1ull;
+      const uint64_t n_words = (n + 31) / 32 + 1, n_bmblk = (n_words + BM_BLOCK - 1) / BM_BLOCK;
+      if ((rc = ensure(X.tkey, X.tkey_cap, (size_t)(nd1 * cap1) * 2 + 32, 1, 1))) return rc;   // 16-byte tuple records (key, position)
+      if ((rc = ensure(X.tkey2, X.tkey2_cap, (size_t)nb * BK_CAP + 32, 1, 1))) return rc;      // the 8-byte bucket tuples
+      if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
+      if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
+      if ((rc = ensure(X.gk, X.gk_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;                 // first position of every distinct k-mer
+      if ((rc = ensure(X.gv, X.gv_cap, (size_t)(2 * n_words + 2 * n_bmblk + 8), 1, 1))) return rc;   // bitmap | word prefix | block sums | block offsets
+      //  small integer scratch: cnt1[nd1] | cnt2[nb] | offs[nb + 1]
+      const size_t iscr = (size_t)nd1 * CNT1_STRIDE + nb + nb + 1 + 16;
+      if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, iscr * 4 + 256))) return rc;
+      unsigned int *cnt1 = reinterpret_cast<unsigned int *>(c->cub_temp), *cnt2 = cnt1 + (size_t)nd1 * CNT1_STRIDE;
+      uint32_t *offs = cnt2 + nb;
+      uint32_t *bitmap = X.gv, *wprefix = bitmap + n_words, *bsum = wprefix + n_words, *boff = bsum + n_bmblk;
+      CK(cudaMemsetAsync(cnt1, 0, ((size_t)nd1 * CNT1_STRIDE + nb) * 4, c->stream));
+      CK(cudaMemsetAsync(bitmap, 0, n_words * 4, c->stream));
+      CK(cudaMemsetAsync(&c->d_work[5], 0, 24, c->stream));              // [5] distinct, [6] overflow flags, [7] partition overflow
+      if (!c->bucket_attr_set) {
+        CK(cudaFuncSetAttribute(k_bucket_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, BK2_SMEM));
+        c->bucket_attr_set = true;
+      }
+      const int sh1 = 2 * K + 3 - B1, sh2 = 2 * K + 3 - B;
+      const uint64_t lowmask = (1ull << sh2) - 1;
+
+      EvTimer t1(c->stream);
+      k_part1<<<div_up(n_groups, PART1_GROUPS), PART_THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, mixc,
+                                                                              sh1, nd1, cap1, reinterpret_cast<uint4 *>(X.tkey), cnt1, &c->d_work[7]);
+      c->launches++;
+      CK(cudaGetLastError());
+      c->timings.index_tuples_ms = t1.stop();
+
       EvTimer t2(c->stream);
-      size_t tb = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tb, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)nt, shift, 2 * K + 3, c->stream);
-      const size_t offs_at = (tb + 255) & ~(size_t)255;
-      if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, offs_at + ((size_t)nb + 1) * 4 + 256))) return rc;
-      uint32_t *offs = reinterpret_cast<uint32_t *>((uint8_t *)c->cub_temp + offs_at);
-      size_t tb2 = tb;
-      //  tkey/tval -> tkey2/occ (partitioned); the grouped positions then go back into tval, which becomes `occ`
-      CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.tkey, X.tkey2, X.tval, X.occ, (int64_t)nt, shift, 2 * K + 3, c->stream));
-      k_bucket_offsets<<<div_up(nb + 1, 256), 256, 0, c->stream>>>(X.tkey2, nt, shift, nb, offs);
-      c->launches += 2 + (B + 7) / 8;
+      k_part2<<<dim3(div_up(cap1, PART_CH), nd1), PART2_THREADS, 0, c->stream>>>(reinterpret_cast<const uint4 *>(X.tkey), cnt1, cap1, sh2, B2, lowmask, posbits, BK_CAP,
+                                                                                X.tkey2, cnt2, &c->d_work[7]);
+      k_bucket_scan<<<1, 1024, 0, c->stream>>>(cnt2, nb, BK_CAP, offs);
+      c->launches += 2;
       CK(cudaGetLastError());
       c->timings.index_sort_ms = t2.stop();
 
       EvTimer t3(c->stream);
-      if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
-      if ((rc = ensure(X.gk, X.gk_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
-      if ((rc = ensure(X.gv, X.gv_cap, (size_t)tmp_cap + 1, 1, 1))) return rc;
-      CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
-      //  per context, not per process: the attribute belongs to the device the context runs on
-      if (!c->bucket_attr_set) { CK(cudaFuncSetAttribute(k_bucket_group, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM)); c->bucket_attr_set = true; }
-      k_bucket_group<<<c->sm_count, BK_THREADS, BK_SMEM, c->stream>>>(X.tkey2, X.occ, offs, nb, K, mix_inv, X.tval, X.tmp_slots,
-                                                                        (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, X.gv, &c->d_work[5]);
+      k_bucket_group2<<<2 * c->sm_count, BK_THREADS, BK2_SMEM, c->stream>>>(X.tkey2, cnt2, offs, nb, K, B, posbits, mix_inv, X.occ, X.tmp_slots,
+                                                                         (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, bitmap, &c->d_work[5]);
       c->launches++;
-      unsigned long long h3[2] = {0, 0};
-      CK(cudaMemcpyAsync(h3, &c->d_work[5], 16, cudaMemcpyDeviceToHost, c->stream));
+      unsigned long long h3[3] = {0, 0, 0}; uint32_t n_occ32 = 0;
+      CK(cudaMemcpyAsync(h3, &c->d_work[5], 24, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(&n_occ32, offs + nb, 4, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       CK(cudaGetLastError());
       c->timings.index_table_ms = t3.stop();
-      if (h3[1] != 0) { bucketed = false; continue; }                     // a bucket did not fit: redo with the sorted build
+      if (h3[1] != 0 || h3[2] != 0) { bucketed = false; continue; }       // a partition or bucket did not fit: redo with the sorted build
       X.n_distinct = h3[0];
-      X.n_occ = nt;
-      std::swap(X.tval, X.occ); std::swap(X.tval_cap, X.occ_cap);        // grouped positions are the occurrence lists
+      X.n_occ = n_occ32;
       X.bucketed = true;
       tmp_ready = true;
       break;
     }
     X.bucketed = false;
+    {
+      EvTimer t1(c->stream);
+      if ((rc = ensure(X.tkey, X.tkey_cap, (size_t)n + 32))) return rc;
+      if ((rc = ensure(X.tkey2, X.tkey2_cap, (size_t)n + 32))) return rc;
+      if ((rc = ensure(X.tval, X.tval_cap, (size_t)n + 32))) return rc;
+      if ((rc = ensure(X.occ, X.occ_cap, (size_t)n + 32))) return rc;
+      if (n_groups) {
+        k_hash_tuples<<<div_up(n_groups, WARPS_PER_BLOCK), THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, X.tkey, X.tval);
+        c->launches++;
+      }
+      CK(cudaGetLastError());
+      c->timings.index_tuples_ms = t1.stop();
+    }
 
     EvTimer t2(c->stream);
     if (n) {
@@ -1280,12 +1534,24 @@ int ovl_build_index(ovlb_ctx *c) {
     if ((rc = ensure(X.gv, X.gv_cap, (size_t)nd + 1, 9, 8))) return rc;
   }
   if ((rc = ensure(X.htab, X.htab_cap, (size_t)hcap, 9, 8))) return rc;
-  if ((rc = ensure(X.gk2, X.gk2_cap, (size_t)nd + 1, 9, 8))) return rc;
-  if ((rc = ensure(X.gv2, X.gv2_cap, (size_t)nd + 1, 9, 8))) return rc;
+  if (!tmp_ready) {
+    if ((rc = ensure(X.gk2, X.gk2_cap, (size_t)nd + 1, 9, 8))) return rc;
+    if ((rc = ensure(X.gv2, X.gv2_cap, (size_t)nd + 1, 9, 8))) return rc;
+  }
   X.hcap = hcap; X.n_slots = (uint32_t)nd;
   CK(cudaMemsetAsync(X.htab, 0xFF, hcap * sizeof(HashEntry), c->stream));
   CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
-  if (X.n_occ) {
+  if (X.n_occ && tmp_ready) {
+    //  path order from the bitmap of first positions (set by k_bucket_group2): prefix popcount, then every distinct k-mer
+    //  places its own slot and publishes it in the hash table
+    const uint64_t n_words = (n + 31) / 32 + 1, n_bmblk = (n_words + BM_BLOCK - 1) / BM_BLOCK;
+    uint32_t *bitmap = X.gv, *wprefix = bitmap + n_words, *bsum = wprefix + n_words, *boff = bsum + n_bmblk;
+    k_bm_blocksum<<<(unsigned)n_bmblk, 256, 0, c->stream>>>(bitmap, n_words, bsum);
+    k_bucket_scan<<<1, 1024, 0, c->stream>>>(bsum, (uint32_t)n_bmblk, 0xFFFFFFFFu, boff);
+    k_bm_prefix<<<(unsigned)n_bmblk, 256, 0, c->stream>>>(bitmap, n_words, boff, wprefix);
+    k_path_slots2<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gk, (uint32_t)nd, bitmap, wprefix, X.slots, X.htab, hcap);
+    c->launches += 4;
+  } else if (X.n_occ) {
     if (!tmp_ready) {
       k_group_heads<<<div_up(X.n_occ, 256), 256, 0, c->stream>>>(X.tkey2, X.occ, (uint32_t)X.n_occ, X.tmp_slots, X.gk, X.gv, &c->d_work[5]);
       c->launches++;

@@ -373,10 +373,11 @@ def test_ingest_random_records_ties_and_edges():
     ov.close()
 
 
-@pytest.mark.parametrize("K", [17, 28])
-def test_other_kmer_lengths_through_the_bucketed_build(K):
+@pytest.mark.parametrize("K,expect_bucketed", [(17, True), (24, True), (28, False)])
+def test_other_kmer_lengths_through_the_bucketed_build(K, expect_bucketed):
     """The index build mixes and buckets the k-mer inside its 2K+3 key bits: check a short and a long K against the
-    oracle on a block large enough for the bucketed build."""
+    oracle on a block large enough for the bucketed build.  The 8-byte bucket tuple holds the key bits below the bucket
+    number next to the position, which always fits for K <= 24; K = 28 takes the sorted build."""
     from oracle import oracle_py as op
     from canu_b200 import synth
     api = _api()
@@ -387,7 +388,7 @@ def test_other_kmer_lengths_through_the_bucketed_build(K):
     pk = api.PackedReads(reads, first_read_id=1, min_len=500)
     ov.load_hash_reads(pk)
     ov.build_index()
-    assert ov.debug_index_info()["bucketed"]
+    assert ov.debug_index_info()["bucketed"] == expect_bucketed
     recs = ov.overlap_ref_batch(pk, cap=1 << 20)
     ctr = ov.counters()
     ov.close()
