@@ -78,7 +78,7 @@ EXPORTS = [
     "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
-    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_assign_tiles",
+    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_kmer_census", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_assign_tiles",
 ]
 
 
@@ -116,6 +116,8 @@ def load_library():
     L.ovlb_debug_extend.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 8 + [C.c_uint32]
     L.ovlb_debug_index_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.ovlb_ingest_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.ovlb_kmer_census.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                   C.POINTER(C.c_uint64), C.c_void_p]
     L.ovlb_params_init.argtypes = [C.POINTER(_Params), C.c_uint32, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.ovlb_params_free.argtypes = [C.POINTER(_Params)]
@@ -336,6 +338,19 @@ class Overlapper:
         n = C.c_uint64()
         _check(self.L.ovlb_ingest_records(self._h, recs.ctypes.data, recs.size, max_evalue, max_id, out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value]
+
+    def kmer_census(self, distinct_fraction=-1.0, min_count=0, slice_bits=0, cap=1 << 20):
+        """Frequent canonical k-mers of the loaded hash reads (the `-k` skip list): (keys, counts, stats)."""
+        while True:
+            keys = np.zeros(cap, dtype=np.uint64); cnts = np.zeros(cap, dtype=np.uint32)
+            n = C.c_uint64(); st = (C.c_uint64 * 4)()
+            rc = self.L.ovlb_kmer_census(self._h, slice_bits, float(distinct_fraction), int(min_count), keys.ctypes.data, cnts.ctypes.data,
+                                         cap, C.byref(n), st)
+            if rc == -3 and n.value >= cap:
+                cap *= 4
+                continue
+            _check(rc)
+            return keys[: n.value], cnts[: n.value], {"distinct": st[0], "present": st[1], "unique": st[2], "threshold": st[3]}
 
     # --- debug taps (tests) ---
     def debug_index_info(self) -> dict:

@@ -13,6 +13,8 @@ int ovl_build_index(ovlb_ctx *c);
 int ovl_seed_ref_batch(ovlb_ctx *c);
 int ovl_extend_pairs(ovlb_ctx *c);
 int ovl_prepare_ext_scratch(ovlb_ctx *c);
+int ovl_kmer_census(ovlb_ctx *c, uint32_t slice_bits, double distinct_fraction, uint64_t min_count,
+                    uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n_out, uint64_t stats[4]);
 int ovl_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
                        ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
 int ovl_debug_extend(ovlb_ctx *c, uint32_t n, const uint32_t *ref_index, const int32_t *dir, const uint32_t *hash_index,
@@ -315,6 +317,15 @@ int ovlb_ingest_records(ovlb_ctx *c, const ovlb_record *in, uint64_t n, uint32_t
   if (!c || !n_out || (n && (!in || !out))) { ovl_set_error("ovlb_ingest_records: null argument"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   return ovl_ingest_records(c, in, n, max_evalue, max_id, out, out_cap, n_out);
+}
+
+int ovlb_kmer_census(ovlb_ctx *c, uint32_t slice_bits, double distinct_fraction, uint64_t min_count,
+                     uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n_out, uint64_t stats[4]) {
+  if (!c || !n_out || (cap && (!kmers || !counts))) { ovl_set_error("ovlb_kmer_census: null argument"); return OVLB_ERR_ARG; }
+  if (distinct_fraction > 1.0) { ovl_set_error("ovlb_kmer_census: distinct_fraction must be <= 1 (negative = off)"); return OVLB_ERR_ARG; }
+  CK(cudaSetDevice(c->device));
+  if (c->hash.cap_reads == 0) { ovl_set_error("ovlb_kmer_census: load the reads with ovlb_load_hash_reads first"); return OVLB_ERR_STATE; }
+  return ovl_kmer_census(c, slice_bits, distinct_fraction, min_count, kmers, counts, cap, n_out, stats);
 }
 
 int ovlb_debug_index_info(ovlb_ctx *c, uint64_t out[4]) {

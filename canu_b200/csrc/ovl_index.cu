@@ -228,9 +228,12 @@ k_hash_tuples(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ wof
 #define BK_CAP     3072                 // tuples of a bucket that fit shared memory
 #define BK_PER     (BK_CAP / BK_THREADS)     // tuples per thread, staged in registers
 #define BK_TARGET  2048                 // mean bucket size the bucket count is chosen for
-#define BK_TABLE_BITS 11
-#define BK_TABLE   (1 << BK_TABLE_BITS) // hash-table entries per bucket
-#define BK_MAXDIST 1792                 // distinct k-mers a bucket may hold (load 0.875)
+//  Hash-table entries per bucket = 2^TB, a template parameter of the bucket kernels: TB = 11 (2048 entries, <= 1792
+//  distinct k-mers, 109 KB of shared memory, two CTAs per SM) serves blocks that cover their genome many times; a block
+//  of a LARGE job covers it a few times at most and nearly every tuple of a bucket is a distinct k-mer: TB = 12 (4096
+//  entries >= BK_CAP, 170 KB, one CTA per SM) can never run out of entries.
+#define BK_TABLE_OF(TB)   (1 << (TB))
+#define BK_MAXDIST_OF(TB) ((1 << (TB)) / 8 * 7)
 
 //  counts distinct k-mers and finds the number of valid tuples in the sorted array
 #define CNT_PER_THREAD 8
@@ -430,11 +433,53 @@ __device__ __forceinline__ bool group_window(uint64_t lo, uint64_t hi, uint64_t 
   return (p + K <= L) && bad == 0;
 }
 
+//  Census only: tuples that do not fit their partition or bucket -- k-mers with thousands to millions of copies, the
+//  very ones the census is after -- are counted in a global open-addressed table instead (key = mixed canonical k-mer),
+//  and the whole bucket of such a k-mer is diverted there (`bucket_spill`, or its count exceeding the capacity), so
+//  that every k-mer is counted in exactly one place.  key == nullptr: not a census (the index build falls back instead).
+struct Spill { unsigned long long *key; unsigned int *cnt; uint64_t mask; unsigned int *bucket_spill; int sh2; unsigned long long *flag; };
+__device__ __forceinline__ void spill_add(const Spill &S, uint64_t km) {
+  uint64_t h = ovl_mix64(km) & S.mask;
+  for (int probe = 0; probe < 4096; probe++) {
+    const unsigned long long cur = S.key[h];
+    if (cur == km) { atomicAdd(&S.cnt[h], 1u); return; }
+    if (cur == ~0ull) {
+      const unsigned long long old = atomicCAS(&S.key[h], ~0ull, (unsigned long long)km);
+      if (old == ~0ull || old == km) { atomicAdd(&S.cnt[h], 1u); return; }
+    }
+    h = (h + 1) & S.mask;
+  }
+  atomicOr(S.flag, 4ull);                                                 // table full
+}
+
+//  reverse complement of a k-mer key (base j in bits 2j..2j+1, A0 C1 G2 T3): complement = ~code, order reversed
+__device__ __forceinline__ uint64_t kmer_rc(uint64_t key, int K) {
+  uint64_t x = __brevll(~key) >> (64 - 2 * K);                            // pairs reversed, bits inside a pair swapped
+  return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+//  CENSUS = k-mer counting for the skip list (ovl_kmer_census): the tuple key is the CANONICAL k-mer (smaller of the
+//  k-mer and its reverse complement), no class, and only the k-mers of slice `slice` of 2^slice_bits (by a hash of the
+//  canonical k-mer) are emitted, so that a store of any size is counted in passes over k-mer space.
+template <bool CENSUS>
+__device__ __forceinline__ bool part1_tuple(uint64_t key, int cls, int K, uint64_t kmask, uint64_t mixc, int slice_bits, uint32_t slice, uint64_t &t) {
+  if (CENSUS) {
+    const uint64_t rc = kmer_rc(key, K);
+    const uint64_t canon = key < rc ? key : rc;
+    if (slice_bits && (uint32_t)(ovl_mix64(canon) >> 40 & ((1u << slice_bits) - 1u)) != slice) return false;
+    t = ((canon * mixc) & kmask) << 3;
+  } else {
+    t = (((key * mixc) & kmask) << 3) | (uint64_t)cls;
+  }
+  return true;
+}
+
+template <bool CENSUS>
 __global__ void __launch_bounds__(PART_THREADS)
 k_part1(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, const uint32_t *__restrict__ len,
         const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read, uint64_t n_groups,
         int K, uint64_t mixc, int sh1, uint32_t nd1, uint64_t cap1,
-        uint4 *__restrict__ trec, unsigned int *cnt1, unsigned long long *flag) {
+        uint4 *__restrict__ trec, unsigned int *cnt1, unsigned long long *flag, int slice_bits, uint32_t slice, Spill S) {
   __shared__ uint32_t hist[PART_MAXD], cursor[PART_MAXD];
   const int tid = threadIdx.x;
   const uint64_t kmask = (1ull << (2 * K)) - 1;
@@ -460,10 +505,9 @@ k_part1(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, con
   __syncthreads();
   for (int w = 0; w < 32; w++) {
     uint64_t key; int cls;
-    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls)) {
-      const uint64_t t = (((key * mixc) & kmask) << 3) | (uint64_t)cls;
+    uint64_t t;
+    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls) && part1_tuple<CENSUS>(key, cls, K, kmask, mixc, slice_bits, slice, t))
       atomicAdd(&hist[(uint32_t)(t >> sh1)], 1u);
-    }
   }
   __syncthreads();
   for (uint32_t d = tid; d < nd1; d += PART_THREADS) { const uint32_t h = hist[d]; cursor[d] = h ? atomicAdd(&cnt1[d * CNT1_STRIDE], h) : 0u; }
@@ -471,11 +515,12 @@ k_part1(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, con
   bool over = false;
   for (int w = 0; w < 32; w++) {
     uint64_t key; int cls;
-    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls)) {
-      const uint64_t t = (((key * mixc) & kmask) << 3) | (uint64_t)cls;
+    uint64_t t;
+    if (group_window(lo, hi, iv, pc0, pi0, w, p0, L, K, kmask, key, cls) && part1_tuple<CENSUS>(key, cls, K, kmask, mixc, slice_bits, slice, t)) {
       const uint32_t d = (uint32_t)(t >> sh1);
       const uint64_t o = atomicAdd(&cursor[d], 1u);
-      if (o < cap1) trec[d * cap1 + o] = make_uint4((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)(g * 32 + w), 0u);
+      if (o < cap1) trec[d * cap1 + o] = make_uint4((uint32_t)t, (uint32_t)(t >> 32), CENSUS ? 0u : (uint32_t)(g * 32 + w), 0u);
+      else if (CENSUS && S.key) { spill_add(S, t >> 3); S.bucket_spill[(uint32_t)(t >> S.sh2)] = 1u; }
       else over = true;
     }
   }
@@ -487,7 +532,7 @@ k_part1(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ woff, con
 __global__ void __launch_bounds__(PART2_THREADS)
 k_part2(const uint4 *__restrict__ trec, const unsigned int *__restrict__ cnt1, uint64_t cap1,
         int sh2, int B2, uint64_t lowmask, int posbits, uint32_t bk_cap,
-        uint64_t *__restrict__ btup, unsigned int *cnt2, unsigned long long *flag) {
+        uint64_t *__restrict__ btup, unsigned int *cnt2, unsigned long long *flag, Spill S) {
   __shared__ uint32_t hist[PART_MAXD], gbase[PART_MAXD];
   const int tid = threadIdx.x;
   const uint32_t p = blockIdx.y;
@@ -523,6 +568,7 @@ k_part2(const uint4 *__restrict__ trec, const unsigned int *__restrict__ cnt1, u
     const uint32_t d = (uint32_t)(t[i] >> sh2) & (nd2 - 1);
     const uint32_t o = gbase[d] + rk[i];
     if (o < bk_cap) btup[(uint64_t)((p << B2) + d) * bk_cap + o] = ((t[i] & lowmask) << posbits) | pos[i];
+    else if (S.key) spill_add(S, t[i] >> 3);                             // census: the bucket's count now exceeds its capacity, which diverts all of it
     else over = true;
   }
   if (over) atomicOr(flag, 1ull);
@@ -577,14 +623,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-#define BK2_SMEM (BK_TABLE * 8 + BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE * 5 * 4 + BK_TABLE * 4 + 64)
+#define BK2_SMEM_OF(TB) (BK_TABLE_OF(TB) * 8 + BK_CAP * 8 + BK_CAP * 4 + BK_CAP * 2 + BK_TABLE_OF(TB) * 5 * 4 + BK_TABLE_OF(TB) * 4 + 64)
 
-//  out[0]: distinct k-mers (slot records emitted), out[1]: bit 0 = a bucket did not fit
-__global__ void __launch_bounds__(BK_THREADS, 2)
+//  out[0]: distinct k-mers (slot records emitted), out[1]: bit 0 = a bucket held more distinct k-mers than the table
+//  takes (retry with the larger table), bit 1 = a bucket or the slot scratch overflowed (sorted build)
+template <int TB>
+__global__ void __launch_bounds__(BK_THREADS, TB == 11 ? 2 : 1)
 k_bucket_group2(const uint64_t *__restrict__ btup, const unsigned int *__restrict__ cnt2, const uint32_t *__restrict__ offs, uint32_t nb,
                 int K, int B, int posbits, uint64_t mix_inv, uint32_t *__restrict__ occ, IndexSlot *__restrict__ tmp, uint32_t tmp_cap,
                 uint32_t *__restrict__ first_pos, uint32_t *first_bitmap, unsigned long long *out) {
   extern __shared__ __align__(128) unsigned char bk_sm[];
+  constexpr int BK_TABLE = BK_TABLE_OF(TB), BK_MAXDIST = BK_MAXDIST_OF(TB);
   uint64_t *hk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_TABLE] low key bits (mixed k-mer below the bucket bits) of the slot
   uint64_t *tbuf = hk + BK_TABLE;                                        // [BK_CAP] the bucket's tuples, filled by the bulk copy
   uint32_t *gpos = reinterpret_cast<uint32_t *>(tbuf + BK_CAP);          // [BK_CAP] positions grouped by (slot, class)
@@ -611,7 +660,7 @@ k_bucket_group2(const uint64_t *__restrict__ btup, const unsigned int *__restric
     uint32_t nxt = b + gridDim.x;
     while (nxt < nb && cnt2[nxt] == 0) nxt += gridDim.x;
     if (m > BK_CAP) {                                                    // cannot happen after a clean k_part2 (it flags the overflow itself)
-      if (tid == 0) atomicOr(&out[1], 1ull);
+      if (tid == 0) atomicOr(&out[1], 2ull);
     }
     const uint32_t s0 = offs[b];
     for (int i = tid; i < BK_TABLE; i += BK_THREADS) { hk[i] = ~0ull; hm[i] = 0xFFFFFFFFu; }
@@ -638,7 +687,7 @@ k_bucket_group2(const uint64_t *__restrict__ btup, const unsigned int *__restric
       const uint32_t pos = (uint32_t)(kreg[j] & posmask);
       const uint32_t cls = (uint32_t)low & 7u;
       const uint64_t km = low >> 3;
-      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> (64 - BK_TABLE_BITS));
+      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> (64 - TB));
       while (true) {
         const uint64_t cur = hk[h];
         if (cur == km) break;
@@ -680,7 +729,7 @@ k_bucket_group2(const uint64_t *__restrict__ btup, const unsigned int *__restric
       const unsigned int nd = n_dist;
       const unsigned long long base = atomicAdd(&out[0], (unsigned long long)nd);
       slot_base = (base + nd <= tmp_cap) ? (unsigned int)base : 0xFFFFFFFFu;
-      if (base + nd > tmp_cap) atomicOr(&out[1], 1ull);
+      if (base + nd > tmp_cap) atomicOr(&out[1], 2ull);
     }
     __syncthreads();
     //  scatter the positions to their segment: hc becomes the END of every (slot, class)
@@ -785,6 +834,114 @@ k_path_slots2(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ fi
   uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
   dst[0] = a; dst[1] = b;
   ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j);
+}
+
+// ------------------------------------------------------------------------------------------------
+//  k-mer census for the skip list: what `meryl count` + `greater-than 1` + `print at-least
+//  distinct=D / threshold=T` compute for Canu (src/pipelines/canu/Meryl.pm:529-533,603-607,663-671; threshold from the
+//  count histogram: src/meryl/src/meryl/merylOp-nextMer.C:103-115).  Same partition kernels as the index build on the
+//  CANONICAL k-mer; one CTA per bucket counts in a shared-memory hash table.  mode 0: histogram of the counts >= 2
+//  (ghist[min(count, CENSUS_HMAX - 1)]); mode 1: the k-mers whose count reaches `thr` are appended to (okey, ocnt).
+// ------------------------------------------------------------------------------------------------
+#define CENSUS_HMAX 65536
+#define CENSUS_TB 12
+#define CENSUS_SMEM (BK_TABLE_OF(CENSUS_TB) * 8 + BK_CAP * 8 + BK_TABLE_OF(CENSUS_TB) * 4 + 64)
+__global__ void __launch_bounds__(BK_THREADS, 2)
+k_bucket_census(const uint64_t *__restrict__ btup, const unsigned int *__restrict__ cnt2, uint32_t nb,
+                int K, int B, int posbits, uint64_t mix_inv, int mode, uint32_t thr,
+                unsigned long long *ghist, uint64_t *okey, uint32_t *ocnt, uint64_t out_cap, unsigned long long *out, Spill S) {
+  extern __shared__ __align__(128) unsigned char bk_sm[];
+  constexpr int BK_TABLE = BK_TABLE_OF(CENSUS_TB), BK_MAXDIST = BK_MAXDIST_OF(CENSUS_TB);
+  uint64_t *hk = reinterpret_cast<uint64_t *>(bk_sm);                    // [BK_TABLE]
+  uint64_t *tbuf = hk + BK_TABLE;                                        // [BK_CAP]
+  uint32_t *hn = reinterpret_cast<uint32_t *>(tbuf + BK_CAP);            // [BK_TABLE] occurrences
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned int n_dist, bad;
+  const int tid = threadIdx.x;
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  const int lowk = 2 * K - B;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  uint32_t b = blockIdx.x;
+  while (b < nb && cnt2[b] == 0) b += gridDim.x;
+  if (tid == 0 && b < nb) bulk_load(tbuf, btup + (uint64_t)b * BK_CAP, ((min(cnt2[b], (unsigned)BK_CAP) * 8u + 15u) & ~15u), &bar);
+  uint32_t parity = 0;
+  while (b < nb) {
+    const uint32_t m = min(cnt2[b], (unsigned)BK_CAP);
+    const bool spilled = cnt2[b] > (unsigned)BK_CAP || S.bucket_spill[b] != 0;
+    uint32_t nxt = b + gridDim.x;
+    while (nxt < nb && cnt2[nxt] == 0) nxt += gridDim.x;
+    for (int i = tid; i < BK_TABLE; i += BK_THREADS) { hk[i] = ~0ull; hn[i] = 0; }
+    if (tid == 0) { n_dist = 0; bad = 0; }
+    mbar_wait(&bar, parity); parity ^= 1;
+    uint64_t kreg[BK_PER];
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) { const uint32_t i = tid + j * BK_THREADS; kreg[j] = i < m ? tbuf[i] : 0ull; }
+    __syncthreads();
+    if (tid == 0 && nxt < nb) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_load(tbuf, btup + (uint64_t)nxt * BK_CAP, ((min(cnt2[nxt], (unsigned)BK_CAP) * 8u + 15u) & ~15u), &bar);
+    }
+    #pragma unroll
+    for (int j = 0; j < BK_PER; j++) {
+      const uint32_t i = tid + j * BK_THREADS;
+      if (i >= m) break;
+      const uint64_t km = (kreg[j] >> posbits) >> 3;
+      if (spilled) { spill_add(S, ((uint64_t)b << lowk) | km); continue; }   // a bucket with an overflowing k-mer is counted in the global table, all of it
+      uint32_t h = (uint32_t)((km * 0xD6E8FEB86659FD93ull) >> (64 - CENSUS_TB));
+      while (true) {
+        const uint64_t cur = hk[h];
+        if (cur == km) break;
+        if (cur == ~0ull) {
+          const unsigned long long old = atomicCAS((unsigned long long *)&hk[h], ~0ull, (unsigned long long)km);
+          if (old == ~0ull) { if (atomicAdd(&n_dist, 1u) >= BK_MAXDIST) bad = 1; break; }
+          if (old == km) break;
+        }
+        if (bad) break;
+        h = (h + 1) & (BK_TABLE - 1);
+      }
+      atomicAdd(&hn[h], 1u);
+    }
+    __syncthreads();
+    if (bad) { if (tid == 0) atomicOr(&out[1], 1ull); }
+    else if (!spilled) {
+      for (int h = tid; h < BK_TABLE; h += BK_THREADS) {
+        const uint64_t kl = hk[h];
+        if (kl == ~0ull) continue;
+        const uint32_t n = hn[h];
+        if (mode == 0) {
+          if (n >= 2) atomicAdd(&ghist[n < CENSUS_HMAX ? n : CENSUS_HMAX - 1], 1ull);
+          else atomicAdd(&ghist[1], 1ull);
+        } else if (n >= thr) {
+          const unsigned long long o = atomicAdd(&out[0], 1ull);
+          if (o < out_cap) { okey[o] = ((((uint64_t)b << lowk) | kl) * mix_inv) & kmask; ocnt[o] = n; }
+          else atomicOr(&out[1], 2ull);
+        }
+      }
+    }
+    __syncthreads();
+    b = nxt;
+  }
+}
+
+//  the k-mers counted in the spill table: same histogram / emission as the bucket entries
+__global__ void __launch_bounds__(256)
+k_spill_scan(Spill S, int K, uint64_t mix_inv, int mode, uint32_t thr, unsigned long long *ghist,
+             uint64_t *okey, uint32_t *ocnt, uint64_t out_cap, unsigned long long *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > S.mask) return;
+  const unsigned long long km = S.key[i];
+  if (km == ~0ull) return;
+  const uint32_t n = S.cnt[i];
+  const uint64_t kmask = (1ull << (2 * K)) - 1;
+  if (mode == 0) {
+    if (n >= 2) atomicAdd(&ghist[n < CENSUS_HMAX ? n : CENSUS_HMAX - 1], 1ull);
+    else atomicAdd(&ghist[1], 1ull);
+  } else if (n >= thr) {
+    const unsigned long long o = atomicAdd(&out[0], 1ull);
+    if (o < out_cap) { okey[o] = (km * mix_inv) & kmask; ocnt[o] = n; }
+    else atomicOr(&out[1], 2ull);
+  }
 }
 
 //  one thread per skip k-mer (the host passes each k-mer once): flag its slot, or append a flagged slot with an empty
@@ -1441,36 +1598,47 @@ int ovl_build_index(ovlb_ctx *c) {
       CK(cudaMemsetAsync(bitmap, 0, n_words * 4, c->stream));
       CK(cudaMemsetAsync(&c->d_work[5], 0, 24, c->stream));              // [5] distinct, [6] overflow flags, [7] partition overflow
       if (!c->bucket_attr_set) {
-        CK(cudaFuncSetAttribute(k_bucket_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, BK2_SMEM));
+        CK(cudaFuncSetAttribute(k_bucket_group2<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK2_SMEM_OF(11)));
+        CK(cudaFuncSetAttribute(k_bucket_group2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK2_SMEM_OF(12)));
         c->bucket_attr_set = true;
       }
       const int sh1 = 2 * K + 3 - B1, sh2 = 2 * K + 3 - B;
       const uint64_t lowmask = (1ull << sh2) - 1;
 
       EvTimer t1(c->stream);
-      k_part1<<<div_up(n_groups, PART1_GROUPS), PART_THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, mixc,
-                                                                              sh1, nd1, cap1, reinterpret_cast<uint4 *>(X.tkey), cnt1, &c->d_work[7]);
+      k_part1<false><<<div_up(n_groups, PART1_GROUPS), PART_THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, mixc,
+                                                                                     sh1, nd1, cap1, reinterpret_cast<uint4 *>(X.tkey), cnt1, &c->d_work[7], 0, 0u, Spill{nullptr, nullptr, 0, nullptr, 0, nullptr});
       c->launches++;
       CK(cudaGetLastError());
       c->timings.index_tuples_ms = t1.stop();
 
       EvTimer t2(c->stream);
       k_part2<<<dim3(div_up(cap1, PART_CH), nd1), PART2_THREADS, 0, c->stream>>>(reinterpret_cast<const uint4 *>(X.tkey), cnt1, cap1, sh2, B2, lowmask, posbits, BK_CAP,
-                                                                                X.tkey2, cnt2, &c->d_work[7]);
+                                                                                X.tkey2, cnt2, &c->d_work[7], Spill{nullptr, nullptr, 0, nullptr, 0, nullptr});
       k_bucket_scan<<<1, 1024, 0, c->stream>>>(cnt2, nb, BK_CAP, offs);
       c->launches += 2;
       CK(cudaGetLastError());
       c->timings.index_sort_ms = t2.stop();
 
       EvTimer t3(c->stream);
-      k_bucket_group2<<<2 * c->sm_count, BK_THREADS, BK2_SMEM, c->stream>>>(X.tkey2, cnt2, offs, nb, K, B, posbits, mix_inv, X.occ, X.tmp_slots,
-                                                                         (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, bitmap, &c->d_work[5]);
-      c->launches++;
       unsigned long long h3[3] = {0, 0, 0}; uint32_t n_occ32 = 0;
-      CK(cudaMemcpyAsync(h3, &c->d_work[5], 24, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaMemcpyAsync(&n_occ32, offs + nb, 4, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      CK(cudaGetLastError());
+      //  the small table first (two CTAs per SM) unless the last block needed the large one; a bucket with more distinct
+      //  k-mers than it takes -- a block that covers its genome only a few times -- reruns this one kernel with TB = 12
+      for (int tb = c->bucket_tb; tb <= 12; tb++) {
+        if (tb == 11) k_bucket_group2<11><<<2 * c->sm_count, BK_THREADS, BK2_SMEM_OF(11), c->stream>>>(X.tkey2, cnt2, offs, nb, K, B, posbits, mix_inv, X.occ, X.tmp_slots,
+                                                                         (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, bitmap, &c->d_work[5]);
+        else          k_bucket_group2<12><<<c->sm_count, BK_THREADS, BK2_SMEM_OF(12), c->stream>>>(X.tkey2, cnt2, offs, nb, K, B, posbits, mix_inv, X.occ, X.tmp_slots,
+                                                                         (uint32_t)std::min<uint64_t>(tmp_cap, 0xFFFFFFFFull), X.gk, bitmap, &c->d_work[5]);
+        c->launches++;
+        CK(cudaMemcpyAsync(h3, &c->d_work[5], 24, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&n_occ32, offs + nb, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        if (h3[1] != 1 || h3[2] != 0 || tb == 12) break;
+        c->bucket_tb = 12;
+        CK(cudaMemsetAsync(bitmap, 0, n_words * 4, c->stream));
+        CK(cudaMemsetAsync(&c->d_work[5], 0, 16, c->stream));
+      }
       c->timings.index_table_ms = t3.stop();
       if (h3[1] != 0 || h3[2] != 0) { bucketed = false; continue; }       // a partition or bucket did not fit: redo with the sorted build
       X.n_distinct = h3[0];
@@ -1746,4 +1914,103 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
   CK(cudaGetLastError());
   c->timings.chain_ms = t4.stop();
   return OVLB_OK;
+}
+
+
+//  k-mer census over the hash reads currently loaded (ovlb_kmer_census): see k_bucket_census.
+//  stats[0] distinct k-mers with count >= 2, [1] their total occurrences, [2] k-mers with count 1, [3] the threshold used.
+int ovl_kmer_census(ovlb_ctx *c, uint32_t slice_bits, double distinct_fraction, uint64_t min_count,
+                    uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n_out, uint64_t stats[4]) {
+  DevReads &H = c->hash;
+  DevIndex &X = c->index;
+  const int K = (int)c->P.kmer_len;
+  const uint64_t n_groups = H.n_pos / 32, n = H.n_pos;
+  int rc;
+  if (slice_bits > 8) { ovl_set_error("ovlb_kmer_census: at most 256 slices"); return OVLB_ERR_ARG; }
+  *n_out = 0;
+  if (n == 0) { if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0; return OVLB_OK; }
+  if ((rc = ensure_groups(c, H))) return rc;
+  const uint64_t per_slice = (n >> slice_bits) + 1;
+  int B = 2 * K + 3 < 8 ? 2 * K + 3 : 8; while (B < 2 * K && (per_slice >> B) > BK_TARGET) B++;
+  if (B < 2) B = 2;
+  const int posbits = 1;                                                  // census tuples carry no position
+  if (2 * K + 3 - B + posbits > 64 || B > 20) { ovl_set_error("ovlb_kmer_census: block too large for one slice; use more slices"); return OVLB_ERR_CAPACITY; }
+  const int B1 = (B + 1) / 2, B2 = B - B1;
+  const uint32_t nd1 = 1u << B1, nb = 1u << B;
+  const uint64_t mean1 = per_slice >> B1;
+  uint64_t cap1 = mean1 + 16 * (uint64_t)sqrt((double)mean1) + PART_CH; cap1 = (cap1 + 1) & ~1ull;
+  if ((rc = ensure(X.tkey, X.tkey_cap, (size_t)(nd1 * cap1) * 2 + 32, 1, 1))) return rc;
+  if ((rc = ensure(X.tkey2, X.tkey2_cap, (size_t)nb * BK_CAP + 32, 1, 1))) return rc;
+  const size_t iscr = (size_t)nd1 * CNT1_STRIDE + nb + 16;
+  if ((rc = ensure((uint8_t *&)c->cub_temp, c->cub_temp_cap, iscr * 4 + 256))) return rc;
+  unsigned int *cnt1 = reinterpret_cast<unsigned int *>(c->cub_temp), *cnt2 = cnt1 + (size_t)nd1 * CNT1_STRIDE;
+  unsigned long long *ghist = nullptr; uint64_t *okey = nullptr; uint32_t *ocnt = nullptr;
+  uint64_t scap = 1ull << 22; while (scap < per_slice / 16) scap <<= 1;
+  Spill S; S.mask = scap - 1; S.sh2 = 2 * K + 3 - B; S.flag = &c->d_work[6];
+  CK(cudaMalloc((void **)&S.key, scap * 8));
+  CK(cudaMalloc((void **)&S.cnt, scap * 4));
+  CK(cudaMalloc((void **)&S.bucket_spill, (size_t)nb * 4));
+  CK(cudaMalloc((void **)&ghist, CENSUS_HMAX * 8));
+  CK(cudaMemsetAsync(ghist, 0, CENSUS_HMAX * 8, c->stream));
+  const uint64_t mixc = 0x9E3779B97F4A7C15ull;
+  uint64_t mix_inv = mixc; for (int i = 0; i < 6; i++) mix_inv *= 2 - mixc * mix_inv;
+  static bool attr_set = false;
+  if (!attr_set) { CK(cudaFuncSetAttribute(k_bucket_census, cudaFuncAttributeMaxDynamicSharedMemorySize, CENSUS_SMEM)); attr_set = true; }
+  const int sh1 = 2 * K + 3 - B1, sh2 = 2 * K + 3 - B;
+  const uint64_t lowmask = (1ull << sh2) - 1;
+  std::vector<unsigned long long> hist(CENSUS_HMAX, 0);
+  uint32_t thr = 0;
+  int result = OVLB_OK;
+  for (int mode = 0; mode < 2 && result == OVLB_OK; mode++) {
+    if (mode == 1) {
+      //  threshold: smallest count v with #{distinct k-mers of count in [2, v]} >= fraction x #{distinct, count >= 2}
+      //  (merylOp-nextMer.C:103-115 over the `greater-than 1` database), AND count >= min_count
+      CK(cudaMemcpyAsync(hist.data(), ghist, CENSUS_HMAX * 8, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      unsigned long long nd = 0, tot = 0;
+      for (uint32_t v = 2; v < CENSUS_HMAX; v++) { nd += hist[v]; tot += hist[v] * v; }
+      uint64_t t_d = 0;
+      if (distinct_fraction >= 0.0) {
+        const unsigned long long target = (unsigned long long)(distinct_fraction * (double)nd);
+        unsigned long long cum = 0;
+        for (uint32_t v = 2; v < CENSUS_HMAX; v++) { if (!hist[v]) continue; cum += hist[v]; if (cum >= target) { t_d = v; break; } }
+      }
+      uint64_t t = std::max<uint64_t>(t_d, min_count);
+      if (t < 2) t = 2;
+      if (t >= CENSUS_HMAX) t = CENSUS_HMAX - 1;      // counts are clamped in the histogram only; emission compares real counts
+      thr = (uint32_t)t;
+      if (stats) { stats[0] = nd; stats[1] = tot; stats[2] = hist[1]; stats[3] = thr; }
+      CK(cudaMalloc((void **)&okey, (cap + 1) * 8));
+      CK(cudaMalloc((void **)&ocnt, (cap + 1) * 4));
+    }
+    CK(cudaMemsetAsync(&c->d_work[5], 0, 24, c->stream));
+    for (uint32_t slice = 0; slice < (1u << slice_bits) && result == OVLB_OK; slice++) {
+      CK(cudaMemsetAsync(cnt1, 0, ((size_t)nd1 * CNT1_STRIDE + nb) * 4, c->stream));
+      CK(cudaMemsetAsync(S.key, 0xFF, scap * 8, c->stream));
+      CK(cudaMemsetAsync(S.cnt, 0, scap * 4, c->stream));
+      CK(cudaMemsetAsync(S.bucket_spill, 0, (size_t)nb * 4, c->stream));
+      k_part1<true><<<div_up(n_groups, PART1_GROUPS), PART_THREADS, 0, c->stream>>>(H.fwd, H.woff, H.len, H.pbase, H.grp_read, n_groups, K, mixc,
+                                                                                    sh1, nd1, cap1, reinterpret_cast<uint4 *>(X.tkey), cnt1, &c->d_work[7], (int)slice_bits, slice, S);
+      k_part2<<<dim3(div_up(cap1, PART_CH), nd1), PART2_THREADS, 0, c->stream>>>(reinterpret_cast<const uint4 *>(X.tkey), cnt1, cap1, sh2, B2, lowmask, posbits, BK_CAP,
+                                                                                X.tkey2, cnt2, &c->d_work[7], S);
+      k_bucket_census<<<2 * c->sm_count, BK_THREADS, CENSUS_SMEM, c->stream>>>(X.tkey2, cnt2, nb, K, B, posbits, mix_inv, mode, thr, ghist, okey, ocnt, cap, &c->d_work[5], S);
+      k_spill_scan<<<div_up(scap, 256), 256, 0, c->stream>>>(S, K, mix_inv, mode, thr, ghist, okey, ocnt, cap, &c->d_work[5]);
+      c->launches += 4;
+      unsigned long long h3[3] = {0, 0, 0};
+      CK(cudaMemcpyAsync(h3, &c->d_work[5], 24, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      CK(cudaGetLastError());
+      if (h3[2] != 0 || (h3[1] & 5)) { ovl_set_error("ovlb_kmer_census: the spill table of high-copy k-mers is full; use more slices"); result = OVLB_ERR_CAPACITY; }
+      else if (h3[1] & 2) { *n_out = h3[0]; ovl_set_error("ovlb_kmer_census: output buffer too small"); result = OVLB_ERR_CAPACITY; }
+      else if (mode == 1) *n_out = h3[0];
+    }
+  }
+  if (result == OVLB_OK && *n_out) {
+    CK(cudaMemcpyAsync(kmers, okey, *n_out * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(counts, ocnt, *n_out * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(ghist); if (okey) cudaFree(okey); if (ocnt) cudaFree(ocnt);
+  cudaFree(S.key); cudaFree(S.cnt); cudaFree(S.bucket_spill);
+  return result;
 }

@@ -28,6 +28,7 @@
 
 #include "../../include/ovlb200.h"
 #include "ovfile.h"
+#include "pack.h"
 #include "sqstore.h"
 
 using namespace ovlhost;
@@ -91,52 +92,6 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 struct Phase { double create = 0, pack_hash = 0, index = 0, pack_ref = 0, stage = 0, run = 0, fetch = 0, submit = 0, destroy = 0, total = 0; };
 
 #define FAIL(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); return 1; } while (0)
-
-//  Pack reads bgn..end (inclusive) of the store into the wire format.  Reads outside the library
-//  filter or shorter than `min_len` keep their slot with length 0 (Build_Hash_Index.C:504-526,
-//  Process_Overlaps.C:55-60).
-struct Packed {
-  std::vector<uint8_t> packed; std::vector<uint64_t> boff; std::vector<uint32_t> len, n_read, n_pos;
-  ovlb_reads view; uint64_t bases = 0;
-};
-
-static bool pack_range(SqStore &S, uint32_t bgn, uint32_t end, uint32_t min_lib, uint32_t max_lib, uint32_t min_len,
-                       Packed &P, std::string &err) {
-  const uint32_t n = end >= bgn ? end - bgn + 1 : 0;
-  P.packed.clear(); P.boff.assign(n, 0); P.len.assign(n, 0); P.n_read.clear(); P.n_pos.clear(); P.bases = 0;
-  std::string bases;
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t id = bgn + i;
-    P.boff[i] = P.packed.size();
-    const uint32_t lib = S.libraryID(id);
-    const uint32_t L = S.readLength(id);
-    if (lib < min_lib || lib > max_lib || L < min_len) continue;
-    int fast = S.appendPacked2bit(id, P.packed, err);
-    if (fast < 0) return false;
-    if (fast == 0) {
-      if (!S.loadRead(id, bases, err)) return false;
-      if (bases.size() != L) { err = "read " + std::to_string(id) + ": decoded length differs from metadata"; return false; }
-      const size_t b0 = P.packed.size();
-      P.packed.resize(b0 + (L + 3) / 4, 0);
-      for (uint32_t j = 0; j < L; j++) {
-        unsigned code;
-        switch (bases[j]) {
-          case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
-          case 'N': code = 0; P.n_read.push_back(i); P.n_pos.push_back(j); break;
-          default: err = "read " + std::to_string(id) + " contains a base that is not ACGTN; this build does not support IUPAC codes"; return false;
-        }
-        P.packed[b0 + (j >> 2)] |= (uint8_t)(code << (6 - 2 * (j & 3)));
-      }
-    }
-    P.len[i] = L;
-    P.bases += L;
-  }
-  P.packed.resize(P.packed.size() + 8, 0);
-  P.view.packed = P.packed.data(); P.view.packed_bytes = P.packed.size() - 8;
-  P.view.byte_offset = P.boff.data(); P.view.len = P.len.data(); P.view.n_reads = n; P.view.first_read_id = bgn;
-  P.view.n_read = P.n_read.data(); P.view.n_pos = P.n_pos.data(); P.view.n_n = P.n_read.size();
-  return true;
-}
 
 //  Packs the read ranges a worker is going to need, in order, on a thread of its own and a few items ahead: reading
 //  and packing a batch from the sqStore costs about as much host time as the GPU needs for it on HiFi-like reads, and

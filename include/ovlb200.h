@@ -292,6 +292,19 @@ int  ovlb_assign_tiles(const ovlb_tile *tiles, uint64_t n_tiles, uint32_t n_work
 int  ovlb_ingest_records(ovlb_ctx *ctx, const ovlb_record *in, uint64_t n, uint32_t max_evalue, uint32_t max_id,
                          ovlb_record *out, uint64_t out_cap, uint64_t *n_out);
 
+/*  The step BEFORE the overlapper: the frequent k-mers Canu passes as `-k <file>`.  Counts the canonical
+ *  k-mers (k = the context's kmer_len) of the reads loaded with ovlb_load_hash_reads and returns those that
+ *  `meryl count | meryl greater-than 1 | meryl print at-least distinct=D at-least threshold=T` would print
+ *  (src/pipelines/canu/Meryl.pm:529-533,603-607,663-671): count >= max(T, the smallest count v such that the k-mers of
+ *  count 2..v are at least the fraction D of all distinct k-mers of count >= 2: src/meryl/src/meryl/merylOp-nextMer.C:103-115).
+ *  distinct_fraction < 0 switches that filter off; min_count 0 likewise.  Each returned key is one member of the
+ *  (k-mer, reverse complement) pair -- the smaller in the A0 C1 G2 T3 encoding -- with base j in bits [2j, 2j+1]; the
+ *  order is unspecified.  The k-mer space is processed in 2^slice_bits passes to bound the scratch memory.
+ *  stats (optional): [0] distinct k-mers of count >= 2, [1] their occurrences, [2] k-mers of count 1, [3] threshold used.
+ *  More than `cap` results: OVLB_ERR_CAPACITY with *n_out = the number found so far.  */
+int  ovlb_kmer_census(ovlb_ctx *ctx, uint32_t slice_bits, double distinct_fraction, uint64_t min_count,
+                      uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n_out, uint64_t stats[4]);
+
 #ifdef __cplusplus
 }
 #endif

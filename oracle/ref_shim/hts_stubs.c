@@ -20,3 +20,13 @@ void *bam_init1(void)                                    { return NULL; }
 void  bam_destroy1(void *b)                              { (void)b; }
 int   sam_read1(void *fp, void *h, void *b)              { (void)fp; (void)h; (void)b; return -1; }
 char *bam_flag2str(int flag)                             { (void)flag; return NULL; }
+
+/*  Named by stores/tgTig.C (BAM output of tig layouts), which ovStoreDump links for its optional -bogart filter;
+ *  dumping an overlap store never reaches them.  */
+int   bam_set1(void *b, ...)                             { (void)b; return -1; }
+int   sam_hdr_add_line(void *h, const char *t, ...)      { (void)h; (void)t; return -1; }
+int   sam_hdr_add_pg(void *h, const char *n, ...)        { (void)h; (void)n; return -1; }
+void *sam_hdr_init(void)                                 { return NULL; }
+int   sam_hdr_write(void *fp, const void *h)             { (void)fp; (void)h; return -1; }
+long  sam_parse_cigar(const char *in, char **end, void *a, void *m) { (void)in; (void)end; (void)a; (void)m; return -1; }
+int   sam_write1(void *fp, const void *h, const void *b) { (void)fp; (void)h; (void)b; return -1; }
