@@ -45,7 +45,8 @@ class _Params(C.Structure):
 class _Reads(C.Structure):
     _fields_ = [("packed", C.c_void_p), ("packed_bytes", C.c_uint64), ("byte_offset", C.c_void_p),
                 ("len", C.c_void_p), ("n_reads", C.c_uint32), ("first_read_id", C.c_uint32),
-                ("n_read", C.c_void_p), ("n_pos", C.c_void_p), ("n_n", C.c_uint64)]
+                ("n_read", C.c_void_p), ("n_pos", C.c_void_p), ("n_n", C.c_uint64),
+                ("src_len", C.c_void_p), ("clear_bgn", C.c_void_p), ("homopoly_compress", C.c_uint32)]
 
 
 class _Counters(C.Structure):
@@ -204,6 +205,42 @@ class PackedReads:
             self.close()
         except Exception:
             pass
+
+
+def homopoly_compress(read: np.ndarray) -> np.ndarray:
+    """Every run of equal bases collapsed to one base (utility/src/sequence/sequence-v1.C:203-261); ASCII uint8 in/out."""
+    r = np.asarray(read, dtype=np.uint8)
+    if r.size == 0:
+        return r
+    keep = np.ones(r.size, dtype=bool)
+    keep[1:] = (r[1:] | 0x20) != (r[:-1] | 0x20)
+    return r[keep]
+
+
+class RawReads(PackedReads):
+    """Reads handed over AS STORED (ovlb_reads.src_len / clear_bgn / homopoly_compress): the device applies homopolymer
+    compression and the clear range.  raw_reads: ASCII arrays (ACGT only); clear: list of (bgn, end) in the coordinates of
+    the (compressed) read, or None for the whole read."""
+
+    def __init__(self, raw_reads, clear=None, homopoly=False, first_read_id=1, min_len=0):
+        super().__init__(raw_reads, first_read_id=first_read_id, min_len=0)
+        n = len(raw_reads)
+        src = np.array([len(r) for r in raw_reads], dtype=np.uint32)
+        cb = np.zeros(n, dtype=np.uint32)
+        out = np.zeros(n, dtype=np.uint32)
+        for i, r in enumerate(raw_reads):
+            full = homopoly_compress(r).size if homopoly else len(r)
+            b, e = clear[i] if clear is not None else (0, full)
+            assert 0 <= b <= e <= full
+            cb[i] = b
+            out[i] = e - b if e - b >= min_len else 0
+        src[out == 0] = 0
+        self._src, self._cb, self._out = src, cb, out
+        v = self.view.contents
+        self._raw_view = _Reads(v.packed, v.packed_bytes, v.byte_offset, out.ctypes.data, v.n_reads, v.first_read_id,
+                                None, None, 0, src.ctypes.data, cb.ctypes.data, 1 if homopoly else 0)
+        self.view = C.pointer(self._raw_view)
+        self.total_bases = int(out.sum())
 
 
 class Overlapper:

@@ -124,7 +124,7 @@ void ovlb_destroy(ovlb_ctx *c) {
   void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.slots, c->index.htab, c->index.tmp_slots, c->index.gk, c->index.gv, c->index.gk2, c->index.gv2,
                    c->index.occ, c->index.tkey, c->index.tkey2, c->index.tval,
                    c->ext.arena, c->ext.row_meta, c->ext.gring, c->ext.path, c->ext.ival, c->ext.ikc, c->ext.ldelta, c->ext.rdelta,
-                   c->stg[0].d_packed, c->stg[0].d_boff, c->stg[0].d_nread, c->stg[0].d_npos,
+                   c->stg[0].d_packed, c->stg[0].d_boff, c->stg[0].d_nread, c->stg[0].d_npos, c->stg[0].d_srclen, c->stg[1].d_srclen,
                    c->stg[1].d_packed, c->stg[1].d_boff, c->stg[1].d_nread, c->stg[1].d_npos, c->ref_valid, c->item_small, c->item_large,
                    c->run_key, c->run_val, c->run_key2, c->run_val2, c->runs_extra, c->pair_flag, c->pair_idx, c->cub_temp, c->pairs,
                    c->seed_start, c->seed_off, c->seed_len, c->sim_nxt, c->sim_hits, c->sim_act, c->sim_order, c->seed_alive, c->d_records };

@@ -123,6 +123,7 @@ struct ovlb_ctx {
     uint8_t  *d_packed = nullptr;   size_t packed_cap = 0;
     uint64_t *d_boff = nullptr;     size_t boff_cap = 0;
     uint32_t *d_nread = nullptr, *d_npos = nullptr; size_t nn_cap = 0;
+    uint32_t *d_srclen = nullptr;   size_t srclen_cap = 0;   // [2n] stored length | clear-range begin of blobs uploaded as stored
     std::vector<uint64_t> h_woff, h_pbase;          // host copies that must outlive the asynchronous upload
   } stg[2];
   cudaStream_t copy_stream = nullptr;

@@ -37,9 +37,10 @@ static inline unsigned div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b
 //  one warp per read: packed 2-bit (4 bases/byte, first base in the top bits) -> dp4 forward words
 __global__ void __launch_bounds__(THREADS)
 k_encode_fwd(const uint8_t *__restrict__ packed, const uint64_t *__restrict__ boff, const uint32_t *__restrict__ len,
-             const uint64_t *__restrict__ woff, uint64_t *__restrict__ fwd, uint32_t n) {
+             const uint64_t *__restrict__ woff, uint64_t *__restrict__ fwd, uint32_t n, const uint32_t *__restrict__ src_len) {
   uint32_t r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= n) return;
+  if (src_len && src_len[r]) return;                    // a stored blob: k_encode_raw prepares it
   const int lane = threadIdx.x & 31;
   const uint32_t L = len[r];
   const uint32_t nw = (L + 15) / 16 + 2;                  // two zero pad words after every read
@@ -64,6 +65,82 @@ k_encode_fwd(const uint8_t *__restrict__ packed, const uint64_t *__restrict__ bo
       }
     }
     dst[w] = out;
+  }
+}
+
+//  One warp per read uploaded AS STORED (ovlb_reads.src_len > 0): homopolymer compression and clear-range trimming on the
+//  device (what sqStore does on the host when it loads a read: decode, homopolyCompress -- utility/src/sequence/
+//  sequence-v1.C:203-261 -- then the clear range, stores/sqStore.H:397-413), straight into dp4 words.  A lane takes 16
+//  consecutive stored bases (one 32-bit load), keeps the first base of every run (the previous lane's last base arrives
+//  by shuffle), a warp scan gives every kept base its position in the compressed read, the lane compacts its kept bases
+//  into one-hot nibbles and ORs them into at most two output words.  `fwd` must be zero where the read goes.
+__global__ void __launch_bounds__(THREADS)
+k_encode_raw(const uint8_t *__restrict__ packed, const uint64_t *__restrict__ boff, const uint32_t *__restrict__ len,
+             const uint64_t *__restrict__ woff, uint64_t *fwd, uint32_t n,
+             const uint32_t *__restrict__ src_len, const uint32_t *__restrict__ clear_bgn, int hpc) {
+  const uint32_t r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const uint32_t S = src_len[r];
+  if (S == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int L = (int)len[r];
+  const int cb = clear_bgn ? (int)clear_bgn[r] : 0;
+  const uint8_t *src = packed + boff[r];
+  unsigned long long *dst = reinterpret_cast<unsigned long long *>(fwd + woff[r]);
+  int c_base = 0;                                       // compressed position of the first base of this round
+  uint32_t prev_code = 4;                               // last base of the previous round (4 = none)
+  for (uint32_t i0 = 0; i0 < S; i0 += 512) {
+    const uint32_t b0 = i0 + 16 * lane;
+    const int nv = b0 < S ? (int)min(16u, S - b0) : 0;
+    uint32_t codes = 0;                                 // base j of the lane in bits [2j, 2j+1]
+    if (nv > 0) {
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t byte = (b0 >> 2) + k;
+        const uint32_t v = (byte < ((S + 3) >> 2)) ? src[byte] : 0u;
+        codes |= ((v >> 6) & 3u) << (8 * k) | ((v >> 4) & 3u) << (8 * k + 2) | ((v >> 2) & 3u) << (8 * k + 4) | (v & 3u) << (8 * k + 6);
+      }
+    }
+    const uint32_t my_last = nv > 0 ? (codes >> (2 * (nv - 1))) & 3u : 4u;
+    uint32_t before = __shfl_up_sync(0xffffffffu, my_last, 1);
+    if (lane == 0) before = prev_code;
+    //  keep mask: every base when not compressing, else the bases that differ from their predecessor
+    uint32_t keep = 0;
+    {
+      uint32_t p = before;
+      #pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const uint32_t cj = (codes >> (2 * j)) & 3u;
+        if (j < nv && (!hpc || cj != p)) keep |= 1u << j;
+        p = cj;
+      }
+    }
+    const int cnt = __popc(keep);
+    int inc = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int o0 = c_base + inc - cnt - cb;                  // output position of my first kept base
+    //  compact the kept bases into one-hot nibbles
+    unsigned long long str = 0; int k2 = 0;
+    #pragma unroll
+    for (int j = 0; j < 16; j++)
+      if ((keep >> j) & 1u) {
+        const int o = o0 + k2;
+        if (o >= 0 && o < L) str |= (unsigned long long)(1u << ((codes >> (2 * j)) & 3u)) << (4 * k2);
+        k2++;
+      }
+    if (str) {
+      //  nibble k2 of `str` belongs at output position o0 + k2 (positions outside [0, L) hold zero nibbles)
+      if (o0 < 0) { str >>= 4 * (-o0); o0 = 0; }
+      const int w = o0 >> 4, sh = (o0 & 15) << 2;
+      if (str << sh) atomicOr(&dst[w], str << sh);
+      if (sh && (str >> (64 - sh))) atomicOr(&dst[w + 1], str >> (64 - sh));
+    }
+    c_base += total;
+    //  last base of the round: the last lane that had bases
+    const unsigned has = __ballot_sync(0xffffffffu, nv > 0);
+    prev_code = __shfl_sync(0xffffffffu, my_last, 31 - __clz(has));
   }
 }
 
@@ -1516,7 +1593,20 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   CK(cudaMemsetAsync(dst.flags, 0, (size_t)(n + 1) * 8, st));
   if (is_hash) CK(cudaEventRecord(e1, st));
   if (n) {
-    k_encode_fwd<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(S.d_packed, S.d_boff, dst.len, dst.woff, dst.fwd, n); c->launches++;
+    const uint32_t *d_src_len = nullptr, *d_clear = nullptr;
+    if (in->src_len) {                                 // blobs as stored: zero the words, then compress / trim on the device
+      if ((rc = ensure(S.d_srclen, S.srclen_cap, (size_t)2 * n + 2))) return rc;
+      CK(cudaMemcpyAsync(S.d_srclen, in->src_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      if (in->clear_bgn) CK(cudaMemcpyAsync(S.d_srclen + n, in->clear_bgn, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      else CK(cudaMemsetAsync(S.d_srclen + n, 0, (size_t)n * 4, st));
+      d_src_len = S.d_srclen; d_clear = S.d_srclen + n;
+      CK(cudaMemsetAsync(dst.fwd, 0, (size_t)(nw + 4) * 8, st));
+    }
+    k_encode_fwd<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(S.d_packed, S.d_boff, dst.len, dst.woff, dst.fwd, n, d_src_len); c->launches++;
+    if (d_src_len) {
+      k_encode_raw<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(S.d_packed, S.d_boff, dst.len, dst.woff, dst.fwd, n, d_src_len, d_clear, (int)in->homopoly_compress);
+      c->launches++;
+    }
     if (in->n_n) { k_apply_n<<<div_up(in->n_n, 256), 256, 0, st>>>(S.d_nread, S.d_npos, in->n_n, dst.woff, dst.len, dst.fwd); c->launches++; }
     k_encode_rc<<<div_up(n, WARPS_PER_BLOCK), THREADS, 0, st>>>(dst.fwd, dst.len, dst.woff, dst.rc, n); c->launches++;
   }

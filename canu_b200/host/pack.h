@@ -12,7 +12,7 @@ namespace ovlhost {
 //  filter or shorter than `min_len` keep their slot with length 0 (Build_Hash_Index.C:504-526,
 //  Process_Overlaps.C:55-60).
 struct Packed {
-  std::vector<uint8_t> packed; std::vector<uint64_t> boff; std::vector<uint32_t> len, n_read, n_pos;
+  std::vector<uint8_t> packed; std::vector<uint64_t> boff; std::vector<uint32_t> len, n_read, n_pos, src_len, clear_bgn;
   ovlb_reads view; uint64_t bases = 0;
 };
 
@@ -20,6 +20,8 @@ inline bool pack_range(SqStore &S, uint32_t bgn, uint32_t end, uint32_t min_lib,
                        Packed &P, std::string &err) {
   const uint32_t n = end >= bgn ? end - bgn + 1 : 0;
   P.packed.clear(); P.boff.assign(n, 0); P.len.assign(n, 0); P.n_read.clear(); P.n_pos.clear(); P.bases = 0;
+  P.src_len.assign(n, 0); P.clear_bgn.assign(n, 0);
+  bool any_raw = false;
   std::string bases;
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t id = bgn + i;
@@ -29,6 +31,12 @@ inline bool pack_range(SqStore &S, uint32_t bgn, uint32_t end, uint32_t min_lib,
     if (lib < min_lib || lib > max_lib || L < min_len) continue;
     int fast = S.appendPacked2bit(id, P.packed, err);
     if (fast < 0) return false;
+    if (fast == 0) {                                                      // homopolymer-compressed store, or a clear range that does not start
+      uint32_t sl = 0, cb = 0;                                            // on a byte: the blob goes up as stored, the device prepares the read
+      fast = S.appendRaw2bit(id, P.packed, sl, cb, err);
+      if (fast < 0) return false;
+      if (fast == 1) { P.src_len[i] = sl; P.clear_bgn[i] = cb; any_raw = true; }
+    }
     if (fast == 0) {
       if (!S.loadRead(id, bases, err)) return false;
       if (bases.size() != L) { err = "read " + std::to_string(id) + ": decoded length differs from metadata"; return false; }
@@ -51,6 +59,8 @@ inline bool pack_range(SqStore &S, uint32_t bgn, uint32_t end, uint32_t min_lib,
   P.view.packed = P.packed.data(); P.view.packed_bytes = P.packed.size() - 8;
   P.view.byte_offset = P.boff.data(); P.view.len = P.len.data(); P.view.n_reads = n; P.view.first_read_id = bgn;
   P.view.n_read = P.n_read.data(); P.view.n_pos = P.n_pos.data(); P.view.n_n = P.n_read.size();
+  P.view.src_len = any_raw ? P.src_len.data() : nullptr; P.view.clear_bgn = any_raw ? P.clear_bgn.data() : nullptr;
+  P.view.homopoly_compress = (S.version() & SQ_COMPRESSED) ? 1u : 0u;
   return true;
 }
 

@@ -205,4 +205,17 @@ int SqStore::appendPacked2bit(uint32_t id, std::vector<uint8_t> &packed, std::st
   return 1;
 }
 
+int SqStore::appendRaw2bit(uint32_t id, std::vector<uint8_t> &packed, uint32_t &src_len, uint32_t &clear_bgn, std::string &err) {
+  if (readLength(id) == 0) return 0;
+  const uint8_t *chunk; uint32_t clen; char enc;
+  if (!fetchChunk(id, chunk, clen, enc, err)) return -1;
+  if (enc != '2') return 0;
+  const uint32_t ulen = ((which_ & SQ_RAW) ? rawu_[id] : coru_[id]).length();
+  if ((uint64_t)clen * 4 < ulen) { err = "read " + std::to_string(id) + ": 2-bit chunk too short"; return -1; }
+  src_len = ulen;
+  clear_bgn = (which_ & SQ_TRIMMED) ? seq(id).clearBgn() : 0;
+  packed.insert(packed.end(), chunk, chunk + ((ulen + 3) >> 2));
+  return 1;
+}
+
 }  // namespace ovlhost

@@ -53,6 +53,11 @@ class SqStore {
   //  without decoding.  Returns 1 if done, 0 if the caller must use loadRead(), -1 on error.
   int appendPacked2bit(uint32_t id, std::vector<uint8_t> &packed, std::string &err);
 
+  //  Second fast path: the read's WHOLE 2-bit blob as stored (src_len bases, before homopolymer compression and
+  //  trimming) for the device to prepare (ovlb_reads.src_len / clear_bgn / homopoly_compress).  Returns 1 if done,
+  //  0 if the blob is not 2-bit (reads with N are stored 3-bit: the caller decodes those with loadRead()), -1 on error.
+  int appendRaw2bit(uint32_t id, std::vector<uint8_t> &packed, uint32_t &src_len, uint32_t &clear_bgn, std::string &err);
+
  private:
   bool readFile(const std::string &name, std::vector<uint8_t> &out, std::string &err) const;
   bool fetchChunk(uint32_t id, const uint8_t *&chunk, uint32_t &chunk_len, char &enc, std::string &err);

@@ -94,6 +94,15 @@ typedef struct {
   const uint32_t *n_read;               /* [n_n] read index of each N                          */
   const uint32_t *n_pos;                /* [n_n] position of each N                            */
   uint64_t        n_n;
+  /*  Optional on-device read preparation: sqStore blobs uploaded AS STORED, homopolymer compression
+   *  (utility/src/sequence/sequence-v1.C:203-261) and clear-range trimming (stores/sqStore.H:397-413) done by the
+   *  device.  For a read with src_len[i] > 0 the packed bytes at byte_offset[i] hold src_len[i] bases as the store
+   *  keeps them; the device first collapses every run of equal bases to one base when homopoly_compress != 0, then
+   *  keeps len[i] bases starting at position clear_bgn[i] of the (compressed) sequence.  src_len == NULL, or
+   *  src_len[i] == 0: the packed bytes already are the final read (and only such reads may appear in the N list).  */
+  const uint32_t *src_len;              /* [n_reads] or NULL                                   */
+  const uint32_t *clear_bgn;            /* [n_reads] or NULL (= 0)                             */
+  uint32_t        homopoly_compress;
 } ovlb_reads;
 
 /*  One overlap, bit-identical to the reference's in-memory ovOverlap

@@ -401,3 +401,34 @@ def test_other_kmer_lengths_through_the_bucketed_build(K, expect_bucketed):
         assert np.array_equal(got[f], want[f]), f
     st = o.stats()
     assert ctr["kmer_hits_with_olap"] == st["kmer_hits_with_olap"] and ctr["kmer_hits_without_olap"] == st["kmer_hits_without_olap"]
+
+
+@pytest.mark.parametrize("homopoly", [False, True])
+def test_reads_prepared_on_the_device_match_reads_prepared_on_the_host(homopoly):
+    """Row f3: sqStore blobs uploaded as stored, homopolymer compression (sequence-v1.C:203-261) and clear-range trimming
+    (sqStore.H:397-413) done by k_encode_raw.  The same reads prepared with numpy and uploaded the ordinary way must
+    give the same records and counters -- clear ranges are random (not byte aligned), a few reads are trimmed to nothing."""
+    from canu_b200 import synth
+    api = _api()
+    g = synth.make_genome(50000, seed=41)
+    raw = synth.simulate_reads(g, 14, 1500, 4500, 0.01, seed=42)
+    rng = np.random.default_rng(43)
+    final, clear = [], []
+    for i, r in enumerate(raw):
+        full = api.homopoly_compress(r) if homopoly else r
+        b = int(rng.integers(0, 40)); e = full.size - int(rng.integers(0, 40))
+        if i % 37 == 0:
+            e = b + 100                                   # shorter than --minlength: dropped on both paths
+        clear.append((b, e)); final.append(np.ascontiguousarray(full[b:e]))
+    prm = api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500, max_read_len=max(r.size for r in raw))
+    out = []
+    for pk in (api.RawReads(raw, clear=clear, homopoly=homopoly, first_read_id=1, min_len=500),
+               api.PackedReads(final, first_read_id=1, min_len=500)):
+        ov = api.Overlapper(prm)
+        ov.load_hash_reads(pk); ov.build_index()
+        recs = np.sort(ov.overlap_ref_batch(pk, cap=1 << 20), order=["a_iid", "b_iid", "w0", "w1"])
+        ctr = ov.counters(); ov.close()
+        out.append((recs, {k: ctr[k] for k in ("pairs", "hash_kmers", "ref_kmers", "seed_hits", "dp_cells", "total_overlaps")}))
+    assert len(out[0][0]) > 300
+    assert out[0][0].tobytes() == out[1][0].tobytes()
+    assert out[0][1] == out[1][1]
