@@ -76,7 +76,7 @@ SEED_DTYPE = np.dtype([("start", "<i4"), ("offset", "<i4"), ("len", "<i4")])
 EXPORTS = [
     "ovlb_last_error", "ovlb_device_count", "ovlb_device_memory", "ovlb_device_total_memory", "ovlb_create", "ovlb_destroy", "ovlb_load_hash_reads",
     "ovlb_mark_skip_kmers", "ovlb_build_index", "ovlb_overlap_ref_batch", "ovlb_stage_ref_batch",
-    "ovlb_run_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
+    "ovlb_run_staged", "ovlb_stage_next_ref_batch", "ovlb_advance_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
     "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_kmer_census", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_assign_tiles",

@@ -4,11 +4,12 @@
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
+#include <utility>
 
 static thread_local std::string g_last_error;
 void ovl_set_error(const std::string &msg) { g_last_error = msg; }
 
-int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_hash, float *upload_ms, float *encode_ms);
+int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, int slot, float *upload_ms, float *encode_ms);
 int ovl_build_index(ovlb_ctx *c);
 int ovl_seed_ref_batch(ovlb_ctx *c);
 int ovl_extend_pairs(ovlb_ctx *c);
@@ -87,6 +88,8 @@ int ovlb_create(int device, const ovlb_params *p, ovlb_ctx **out) {
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming));
   CK(cudaEventCreate(&c->ref_up0)); CK(cudaEventCreate(&c->ref_up1));
+  CK(cudaEventCreateWithFlags(&c->next_ready, cudaEventDisableTiming));
+  CK(cudaEventCreate(&c->next_up0)); CK(cudaEventCreate(&c->next_up1));
   CK(cudaMalloc((void **)&c->d_eml, (size_t)p->n_edit_match_limit * 4));
   CK(cudaMemcpyAsync(c->d_eml, p->edit_match_limit, (size_t)p->n_edit_match_limit * 4, cudaMemcpyHostToDevice, c->stream));
   c->P.edit_match_limit = nullptr;                     // caller's buffer is not retained
@@ -120,7 +123,10 @@ void ovlb_destroy(ovlb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-  free_reads(c->hash); free_reads(c->ref);
+  free_reads(c->hash); free_reads(c->ref); free_reads(c->ref_next);
+  { void *np[] = { c->stg_next.d_packed, c->stg_next.d_boff, c->stg_next.d_nread, c->stg_next.d_npos, c->stg_next.d_srclen };
+    for (void *p : np) if (p) cudaFree(p); }
+  if (c->next_ready) { cudaEventDestroy(c->next_ready); cudaEventDestroy(c->next_up0); cudaEventDestroy(c->next_up1); }
   void *ptrs[] = { c->d_eml, c->d_counters, c->d_work, c->index.slots, c->index.htab, c->index.tmp_slots, c->index.gk, c->index.gv, c->index.gk2, c->index.gv2,
                    c->index.occ, c->index.tkey, c->index.tkey2, c->index.tval,
                    c->ext.arena, c->ext.row_meta, c->ext.gring, c->ext.path, c->ext.ival, c->ext.ikc, c->ext.ldelta, c->ext.rdelta,
@@ -142,7 +148,7 @@ int ovlb_load_hash_reads(ovlb_ctx *c, const ovlb_reads *reads) {
   if (reads->n_reads >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
   c->index.built = false;
   c->skip_keys.clear();
-  return ovl_upload_reads(c, reads, c->hash, true, &c->timings.upload_ms, &c->timings.encode_ms);
+  return ovl_upload_reads(c, reads, c->hash, 0, &c->timings.upload_ms, &c->timings.encode_ms);
 }
 
 int ovlb_mark_skip_kmers(ovlb_ctx *c, const uint64_t *keys, uint64_t n) {
@@ -168,9 +174,32 @@ int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
   if (reads->n_reads >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   CK(cudaSetDevice(c->device));
   c->staged = false;
-  int rc = ovl_upload_reads(c, reads, c->ref, false, &c->timings.upload_ms, &c->timings.encode_ms);
+  int rc = ovl_upload_reads(c, reads, c->ref, 1, &c->timings.upload_ms, &c->timings.encode_ms);
   if (rc) return rc;
   c->staged = true;
+  return OVLB_OK;
+}
+
+int ovlb_stage_next_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
+  if (!c || !reads) { ovl_set_error("ovlb_stage_next_ref_batch: null argument"); return OVLB_ERR_ARG; }
+  if (reads->n_reads >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
+  if (c->staged_next) { ovl_set_error("ovlb_stage_next_ref_batch: a next batch is already staged; call ovlb_advance_staged first"); return OVLB_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  float up = 0, en = 0;
+  int rc = ovl_upload_reads(c, reads, c->ref_next, 2, &up, &en);
+  if (rc) return rc;
+  c->staged_next = true;
+  return OVLB_OK;
+}
+
+int ovlb_advance_staged(ovlb_ctx *c) {
+  if (!c) { ovl_set_error("ovlb_advance_staged: null context"); return OVLB_ERR_ARG; }
+  std::swap(c->ref, c->ref_next);
+  std::swap(c->stg[1], c->stg_next);
+  std::swap(c->ref_ready, c->next_ready); std::swap(c->ref_up0, c->next_up0); std::swap(c->ref_up1, c->next_up1);
+  std::swap(c->ref_pending, c->next_pending);
+  c->staged = c->staged_next;
+  c->staged_next = false;
   return OVLB_OK;
 }
 

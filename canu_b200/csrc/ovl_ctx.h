@@ -129,6 +129,12 @@ struct ovlb_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t  ref_ready = nullptr, ref_up0 = nullptr, ref_up1 = nullptr;   // ref upload + encode done; brackets for its timing
   bool         ref_pending = false;                   // a ref upload is in flight on copy_stream
+  //  second ref slot (ovlb_stage_next_ref_batch): batch i+1 is uploaded and encoded on the copy stream while batch i runs;
+  //  ovlb_advance_staged swaps the slots
+  DevReads     ref_next;
+  Staging      stg_next;
+  cudaEvent_t  next_ready = nullptr, next_up0 = nullptr, next_up1 = nullptr;
+  bool         next_pending = false, staged_next = false;
   uint8_t  *h_pinned = nullptr;   size_t pinned_cap = 0;
   std::vector<uint64_t> skip_keys;
 

@@ -1521,7 +1521,11 @@ struct EvTimer {
 };
 
 //  Upload + encode a read set (host pointers) into `dst`.  `is_hash`: flags are per read, else per (read,dir).
-int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_hash, float *upload_ms, float *encode_ms) {
+//  slot: 0 = hash block, 1 = ref batch, 2 = the NEXT ref batch (second slot, uploaded while slot 1 runs)
+int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, int slot, float *upload_ms, float *encode_ms) {
+  const bool is_hash = slot == 0;
+  bool &pending = slot == 2 ? c->next_pending : c->ref_pending;
+  cudaEvent_t ev_ready = slot == 2 ? c->next_ready : c->ref_ready, ev_up0 = slot == 2 ? c->next_up0 : c->ref_up0, ev_up1 = slot == 2 ? c->next_up1 : c->ref_up1;
   if (!in || (in->n_reads && (!in->byte_offset || !in->len))) { ovl_set_error("ovl_upload_reads: null argument"); return OVLB_ERR_ARG; }
   const uint32_t n = in->n_reads;
   std::vector<uint64_t> woff(n + 1), pbase(n + 1);
@@ -1542,7 +1546,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   if (maxlen > c->P.max_read_len) { ovl_set_error("read longer than ovlb_params.max_read_len"); return OVLB_ERR_ARG; }
 
   int rc;
-  if (!is_hash && c->ref_pending) { CK(cudaStreamSynchronize(c->copy_stream)); c->ref_pending = false; }   // previous upload still in flight
+  if (!is_hash && pending) { CK(cudaStreamSynchronize(c->copy_stream)); pending = false; }   // previous upload into this slot still in flight
   if (nw + 4 > dst.cap_words) {
     if (dst.fwd) cudaFree(dst.fwd); if (dst.rc) cudaFree(dst.rc);
     dst.fwd = dst.rc = nullptr; dst.cap_words = 0;
@@ -1565,7 +1569,7 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   //  Hash side: on the compute stream, synchronous (the index build follows).  Ref side: on the copy stream, asynchronous
   //  when the caller's buffers are page-locked -- it overlaps the index build or the previous batch's host work;
   //  ovlb_run_staged makes the compute stream wait for `ref_ready`.
-  ovlb_ctx::Staging &S = c->stg[is_hash ? 0 : 1];
+  ovlb_ctx::Staging &S = slot == 2 ? c->stg_next : c->stg[is_hash ? 0 : 1];
   cudaStream_t st = is_hash ? c->stream : c->copy_stream;
   S.h_woff.swap(woff); S.h_pbase.swap(pbase);
   if ((rc = ensure(S.d_packed, S.packed_cap, (size_t)in->packed_bytes + 16))) return rc;
@@ -1578,14 +1582,16 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (is_hash) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); CK(cudaEventRecord(e0, st)); }
-  else CK(cudaEventRecord(c->ref_up0, st));
-  if (in->packed_bytes) CK(cudaMemcpyAsync(S.d_packed, in->packed, in->packed_bytes, cudaMemcpyHostToDevice, st));
+  else CK(cudaEventRecord(ev_up0, st));
+  //  the small per-read arrays first (from pageable memory these copies are synchronous: they must not queue behind
+  //  the large one), then the packed bases, asynchronous when the caller page-locked them
   if (n) {
     CK(cudaMemcpyAsync(S.d_boff, in->byte_offset, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(dst.len, in->len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   }
   CK(cudaMemcpyAsync(dst.woff, S.h_woff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dst.pbase, S.h_pbase.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (in->packed_bytes) CK(cudaMemcpyAsync(S.d_packed, in->packed, in->packed_bytes, cudaMemcpyHostToDevice, st));
   if (in->n_n) {
     CK(cudaMemcpyAsync(S.d_nread, in->n_read, in->n_n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(S.d_npos, in->n_pos, in->n_n * 4, cudaMemcpyHostToDevice, st));
@@ -1619,9 +1625,9 @@ int ovl_upload_reads(ovlb_ctx *c, const ovlb_reads *in, DevReads &dst, bool is_h
     cudaEventElapsedTime(&ms, e1, e2); if (encode_ms) *encode_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   } else {
-    CK(cudaEventRecord(c->ref_up1, st));
-    CK(cudaEventRecord(c->ref_ready, st));
-    c->ref_pending = true;
+    CK(cudaEventRecord(ev_up1, st));
+    CK(cudaEventRecord(ev_ready, st));
+    pending = true;
   }
   (void)is_hash;
   return OVLB_OK;

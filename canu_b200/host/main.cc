@@ -108,6 +108,11 @@ class Prefetcher {
   //  hand a consumed batch back: its buffers (already faulted in, already big enough) are reused for a later item --
   //  first-touch page faults on fresh vectors cost 9x the packing itself (2.3 vs 20 Gbases/s measured)
   void recycle(std::unique_ptr<Packed> p) { if (!p) return; std::lock_guard<std::mutex> lk(mu_); free_.push_back(std::move(p)); }
+  //  a recycled (or new) batch object for a caller that packs by itself (halves of an overflowed batch)
+  std::unique_ptr<Packed> spare() {
+    { std::lock_guard<std::mutex> lk(mu_); if (!free_.empty()) { auto p = std::move(free_.back()); free_.pop_back(); return p; } }
+    return std::unique_ptr<Packed>(new Packed());
+  }
   //  next item of the plan; nullptr + err on failure
   std::unique_ptr<Packed> next(std::string &err) {
     std::unique_lock<std::mutex> lk(mu_);
@@ -170,6 +175,29 @@ static int load_skip_kmers(const char *fn, uint32_t K, std::vector<uint64_t> &ke
   fprintf(stderr, "\nRead %d kmers to mark to skip\n\n", kmerNum);
   return 0;
 }
+
+//  Page-locked record buffers cycling between the workers (device -> host copies land here at full speed) and the
+//  writer threads (which hand a buffer back as soon as they have consumed its records).
+class RecPool {
+ public:
+  struct Buf { std::vector<ovlb_record> v; const void *reg = nullptr; size_t reg_bytes = 0; };
+  explicit RecPool(size_t n) { for (size_t i = 0; i < n; i++) free_.push_back(new Buf()); total_ = n; }
+  ~RecPool() { drain(); for (Buf *b : free_) { if (b->reg) ovlb_host_unregister(b->reg); delete b; } }
+  Buf *acquire(uint64_t n_records) {
+    Buf *b;
+    { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [this] { return !free_.empty(); }); b = free_.back(); free_.pop_back(); }
+    if (b->v.size() < n_records + 1) {
+      if (b->reg) { ovlb_host_unregister(b->reg); b->reg = nullptr; }
+      b->v.resize(std::max<size_t>((size_t)(n_records * 3 / 2) + 1024, 1u << 20));
+      if (ovlb_host_register(b->v.data(), b->v.size() * sizeof(ovlb_record)) == 0) { b->reg = b->v.data(); b->reg_bytes = b->v.size() * sizeof(ovlb_record); }
+    }
+    return b;
+  }
+  void release(Buf *b) { { std::lock_guard<std::mutex> lk(mu_); free_.push_back(b); } cv_.notify_one(); }
+  void drain() { std::unique_lock<std::mutex> lk(mu_); cv_.wait(lk, [this] { return free_.size() == total_; }); }
+ private:
+  std::mutex mu_; std::condition_variable cv_; std::vector<Buf *> free_; size_t total_ = 0;
+};
 
 int main(int argc, char **argv) {
   Options G;
@@ -308,7 +336,9 @@ int main(int argc, char **argv) {
   const uint32_t W = (uint32_t)G.gpus.size();
 
   OvFileWriter out;
-  if (!out.open(G.outName, N, e)) FAIL("ERROR: %s", e.c_str());
+  //  compression threads of the writer: HiFi-like jobs produce ~0.6 GB/s of records per GPU (26 MB per 45 ms tile)
+  const unsigned writerThreads = (unsigned)std::max<size_t>(2, std::min<size_t>(16, 2 * G.gpus.size()));
+  if (!out.open(G.outName, N, e, writerThreads)) FAIL("ERROR: %s", e.c_str());
 
   //  Re-block the job inside the process (the output does not depend on blocking): hash blocks
   //  sized for HBM, ref batches sized for the device seed buffers -- and small enough that every GPU gets several.
@@ -466,11 +496,39 @@ int main(int argc, char **argv) {
     }
     if (ovlb_create(G.gpus[wi], &Pw, &ctx)) { werr[wi] = ovlb_last_error(); return; }
     ph.create += now_s() - t0;
-    std::unique_ptr<Packed> HBp, RBp;
-    Packed RBsplit;                                                     // halves of an overflowed batch are packed here, synchronously
+    std::unique_ptr<Packed> HBp;
     uint32_t curHb = 0, curHe = 0;
-    std::vector<ovlb_record> recs;
-    std::vector<std::pair<uint32_t, uint32_t>> todo;                    // ref ranges of the current tile (split on overflow)
+    //  Ref batches of the tiles of the current hash block, pipelined: while batch i runs, batch i+1 is
+    //  already packed (prefetch thread), page-locked and being uploaded + encoded on the copy stream into the context's
+    //  second ref slot; its records come back into a page-locked buffer that a writer thread hands back when it has
+    //  consumed them.  A batch that overflows the device's seed buffers is cut in two and re-queued.
+    struct Work { uint32_t rb, re; bool planned; };
+    struct Staged { std::unique_ptr<Packed> own; uint32_t rb = 0, re = 0; };
+    std::deque<Work> q;
+    auto pin = [&](Packed &P) {                                           // page-lock the batch (once per buffer: recycled buffers keep their storage)
+      //  only the packed bases (the per-read arrays are a few hundred KB and go first, see ovl_upload_reads): every
+      //  cudaHostRegister costs tens of milliseconds whatever the size (measured: 25 registrations = 0.7 s)
+      const void *ptrs[5] = { P.packed.data(), nullptr, nullptr, nullptr, nullptr };
+      const size_t bytes[5] = { P.packed.capacity(), 0, 0, 0, 0 };
+      for (int k = 0; k < 1; k++) {
+        if (P.pinned[k].first == ptrs[k] && P.pinned[k].second == bytes[k]) continue;
+        if (P.pinned[k].first) ovlb_host_unregister(P.pinned[k].first);
+        P.pinned[k] = {nullptr, 0};
+        if (ptrs[k] && bytes[k] && ovlb_host_register(ptrs[k], bytes[k]) == 0) P.pinned[k] = {ptrs[k], bytes[k]};
+      }
+    };
+    auto take = [&](Staged &S, std::string &err) -> bool {                // next batch of the queue, packed and pinned
+      const Work w = q.front(); q.pop_front();
+      double t1 = now_s();
+      if (w.planned) { S.own = pf.next(err); if (!S.own) return false; }
+      else { S.own = pf.spare(); if (!pack_range(st, w.rb, w.re, G.minLibToRef, G.maxLibToRef, minLen, *S.own, err)) return false; }
+      S.rb = w.rb; S.re = w.re;
+      ph.pack_ref += now_s() - t1; t1 = now_s();
+      pin(*S.own);
+      ph.stage += now_s() - t1;
+      return true;
+    };
+    RecPool pool(3);
     for (size_t ti = 0; ti < tiles.size() && werr[wi].empty(); ti++) {
       if (owner[ti] != wi) continue;
       const ovlb_tile &T = tiles[ti];
@@ -488,41 +546,64 @@ int main(int argc, char **argv) {
         ph.index += now_s() - t0;
         curHb = T.hash_bgn; curHe = T.hash_end;
       }
+      //  all of this worker's tiles of this hash block, in plan order (the prefetcher packs them in that order);
       //  only ref reads with ID below the last hash read can produce pairs (refID < hashID)
-      const uint32_t re = std::min(T.ref_end, T.hash_end > 0 ? T.hash_end - 1 : 0);
-      todo.clear();
-      if (T.ref_bgn <= re) todo.push_back({T.ref_bgn, re});
-      bool first = true;
-      while (!todo.empty() && werr[wi].empty()) {
-        const uint32_t rb = todo.back().first, r2 = todo.back().second;
-        todo.pop_back();
+      q.clear();
+      size_t tj = ti;
+      for (; tj < tiles.size(); tj++) {
+        if (owner[tj] != wi) continue;
+        if (tiles[tj].hash_bgn != curHb || tiles[tj].hash_end != curHe) break;
+        const uint32_t re = std::min(tiles[tj].ref_end, tiles[tj].hash_end > 0 ? tiles[tj].hash_end - 1 : 0);
+        if (tiles[tj].ref_bgn <= re) q.push_back({tiles[tj].ref_bgn, re, true});
+        ti = tj;
+      }
+      Staged A, B;
+      bool haveA = false;
+      if (!q.empty()) {
+        if (!take(A, err)) { werr[wi] = err; break; }
         t0 = now_s();
-        if (first) { pf.recycle(std::move(RBp)); RBp = pf.next(err); if (!RBp) { werr[wi] = err; break; } }
-        else if (!pack_range(st, rb, r2, G.minLibToRef, G.maxLibToRef, minLen, RBsplit, err)) { werr[wi] = err; break; }
-        Packed &RB = first ? *RBp : RBsplit;
-        first = false;
-        ph.pack_ref += now_s() - t0; t0 = now_s();
-        uint64_t n = 0;
-        int rc = ovlb_stage_ref_batch(ctx, &RB.view);
-        ph.stage += now_s() - t0; t0 = now_s();
-        if (!rc) rc = ovlb_run_staged(ctx, &n);
-        ph.run += now_s() - t0; t0 = now_s();
-        if (rc == OVLB_ERR_CAPACITY && r2 > rb) {                       // seed buffers overflowed: halve the batch
-          const uint32_t mid = rb + (r2 - rb) / 2;
-          todo.push_back({mid + 1, r2}); todo.push_back({rb, mid});
-          continue;
+        if (ovlb_stage_ref_batch(ctx, &A.own->view)) { werr[wi] = ovlb_last_error(); break; }
+        ph.stage += now_s() - t0;
+        haveA = true;
+      }
+      while (haveA && werr[wi].empty()) {
+        bool haveB = false;
+        if (!q.empty()) {
+          if (!take(B, err)) { werr[wi] = err; break; }
+          t0 = now_s();
+          if (ovlb_stage_next_ref_batch(ctx, &B.own->view)) { werr[wi] = ovlb_last_error(); break; }
+          ph.stage += now_s() - t0;
+          haveB = true;
         }
-        if (rc) { werr[wi] = ovlb_last_error(); break; }
-        recs.resize(n);
-        if (ovlb_fetch_records(ctx, recs.data(), recs.size(), &n)) { werr[wi] = ovlb_last_error(); break; }
-        ph.fetch += now_s() - t0;
-        { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", phys(G.gpus[wi]), rb, r2, T.hash_bgn, T.hash_end, (unsigned long)RB.bases, (unsigned long)n); }
         t0 = now_s();
-        out.submit(std::move(recs));
-        recs = std::vector<ovlb_record>();
-        ph.submit += now_s() - t0;
+        uint64_t n = 0;
+        int rc = ovlb_run_staged(ctx, &n);
+        ph.run += now_s() - t0; t0 = now_s();
+        if (rc == OVLB_ERR_CAPACITY && A.re > A.rb) {                     // seed buffers overflowed: halve the batch, re-queue
+          const uint32_t mid = A.rb + (A.re - A.rb) / 2;
+          q.push_front({mid + 1, A.re, false}); q.push_front({A.rb, mid, false});
+        } else if (rc) { werr[wi] = ovlb_last_error(); break; }
+        else {
+          RecPool::Buf *rb = pool.acquire(n);
+          if (ovlb_fetch_records(ctx, rb->v.data(), rb->v.size(), &n)) { werr[wi] = ovlb_last_error(); pool.release(rb); break; }
+          ph.fetch += now_s() - t0;
+          { std::lock_guard<std::mutex> lk(log_mu); fprintf(stderr, "[gpu %d] Processed reads %u-%u against %u-%u (%lu bases): %lu overlaps\n", phys(G.gpus[wi]), A.rb, A.re, curHb, curHe, (unsigned long)A.own->bases, (unsigned long)n); }
+          t0 = now_s();
+          out.submit(rb->v.data(), n, [&pool, rb] { pool.release(rb); });
+          ph.submit += now_s() - t0;
+        }
+        if (ovlb_advance_staged(ctx)) { werr[wi] = ovlb_last_error(); break; }
+        pf.recycle(std::move(A.own));
+        if (haveB) { A = std::move(B); }
+        else if (!q.empty()) {                                            // only halves of an overflowed batch are left
+          if (!take(A, err)) { werr[wi] = err; break; }
+          t0 = now_s();
+          if (ovlb_stage_ref_batch(ctx, &A.own->view)) { werr[wi] = ovlb_last_error(); break; }
+          ph.stage += now_s() - t0;
+        } else haveA = false;
       }
     }
+    pool.drain();
     if (werr[wi].empty() && ovlb_get_counters(ctx, &counters[wi])) werr[wi] = ovlb_last_error();
     //  The context is NOT destroyed: the process _exit()s right after the outputs are closed, and freeing tens of GB
     //  buffer by buffer (every cudaFree synchronises the device) cost 0.2 - 2 s per worker for nothing.

@@ -1,5 +1,6 @@
 #include "ovfile.h"
 
+#include <algorithm>
 #include <cstring>
 #include <sys/stat.h>
 
@@ -116,11 +117,13 @@ bool snappy_uncompress(const uint8_t *in, size_t n, std::vector<uint8_t> &out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-//  writer
+//  writer: a pool of threads, each turns whole batches into blocks (transpose to the 6-word record, snappy, one
+//  fwrite under the file lock).  Blocks are independent and record order is unspecified (the reference's own order
+//  depends on its thread interleaving), so nothing has to be re-ordered; the per-read counts are atomic adds.
 // ---------------------------------------------------------------------------------------------
-OvFileWriter::~OvFileWriter() { std::string e; if (file_ || th_.joinable()) close(e); }
+OvFileWriter::~OvFileWriter() { std::string e; if (file_ || !th_.empty()) close(e); }
 
-bool OvFileWriter::open(const std::string &name, uint32_t last_read_id, std::string &err) {
+bool OvFileWriter::open(const std::string &name, uint32_t last_read_id, std::string &err, unsigned n_threads) {
   name_ = name;
   //  findBaseFileName: strip everything from the first '.' after the last '/', unless `name` is a directory
   std::string prefix = name;
@@ -135,55 +138,65 @@ bool OvFileWriter::open(const std::string &name, uint32_t last_read_id, std::str
   if (!file_) { err = "cannot open '" + name + "' for writing"; return false; }
   setvbuf(file_, nullptr, _IOFBF, 1 << 22);
   opr_.assign((size_t)last_read_id + 1, 0);
-  block_.reserve(kBlockWords);
-  th_ = std::thread(&OvFileWriter::run, this);
+  if (n_threads == 0) n_threads = 1;
+  for (unsigned t = 0; t < n_threads; t++) th_.emplace_back(&OvFileWriter::run, this);
   return true;
 }
 
 void OvFileWriter::submit(std::vector<ovlb_record> &&batch) {
   if (batch.empty()) return;
-  { std::lock_guard<std::mutex> lk(mu_); q_.push_back(std::move(batch)); }
+  auto *v = new std::vector<ovlb_record>(std::move(batch));
+  submit(v->data(), v->size(), [v] { delete v; });
+}
+
+void OvFileWriter::submit(const ovlb_record *recs, size_t n, std::function<void()> done) {
+  if (n == 0) { if (done) done(); return; }
+  { std::lock_guard<std::mutex> lk(mu_); q_.push_back(Batch{recs, n, std::move(done)}); }
   cv_.notify_one();
 }
 
-void OvFileWriter::flushBlock() {
-  if (block_.empty() || failed_) { block_.clear(); return; }
-  const size_t nbytes = block_.size() * 4;
-  comp_.resize(snappy_max_compressed(nbytes));
-  uint64_t cl = snappy_compress((const uint8_t *)block_.data(), nbytes, comp_.data());
-  if (fwrite(&cl, 8, 1, file_) != 1 || fwrite(comp_.data(), 1, cl, file_) != cl) { failed_ = true; err_ = "write to '" + name_ + "' failed"; }
-  block_.clear();
-}
-
 void OvFileWriter::run() {
+  std::vector<uint32_t> block; block.reserve(kBlockWords);
+  std::vector<uint8_t> comp;
   while (true) {
-    std::vector<ovlb_record> batch;
+    Batch b;
     {
       std::unique_lock<std::mutex> lk(mu_);
       cv_.wait(lk, [&] { return done_ || !q_.empty(); });
       if (q_.empty()) break;
-      batch = std::move(q_.front());
+      b = std::move(q_.front());
       q_.pop_front();
     }
-    for (const ovlb_record &r : batch) {
-      if (block_.size() + 6 > kBlockWords) flushBlock();
-      block_.push_back(r.a_iid);
-      block_.push_back(r.b_iid);
-      block_.push_back((uint32_t)(r.dat0 >> 32)); block_.push_back((uint32_t)r.dat0);
-      block_.push_back((uint32_t)(r.dat1 >> 32)); block_.push_back((uint32_t)r.dat1);
-      if (r.a_iid < opr_.size()) opr_[r.a_iid]++;
-      if (r.b_iid < opr_.size()) opr_[r.b_iid]++;
-      n_olaps_++;
+    const size_t per_block = kBlockWords / 6;
+    for (size_t i0 = 0; i0 < b.n; i0 += per_block) {
+      const size_t m = std::min(per_block, b.n - i0);
+      block.clear();
+      for (size_t i = i0; i < i0 + m; i++) {
+        const ovlb_record &r = b.recs[i];
+        block.push_back(r.a_iid);
+        block.push_back(r.b_iid);
+        block.push_back((uint32_t)(r.dat0 >> 32)); block.push_back((uint32_t)r.dat0);
+        block.push_back((uint32_t)(r.dat1 >> 32)); block.push_back((uint32_t)r.dat1);
+        if (r.a_iid < opr_.size()) __atomic_fetch_add(&opr_[r.a_iid], 1u, __ATOMIC_RELAXED);
+        if (r.b_iid < opr_.size()) __atomic_fetch_add(&opr_[r.b_iid], 1u, __ATOMIC_RELAXED);
+      }
+      if (i0 + m == b.n && b.done) { b.done(); b.done = nullptr; }       // records consumed: the caller's buffer is free again
+      const size_t nbytes = block.size() * 4;
+      comp.resize(snappy_max_compressed(nbytes));
+      const uint64_t cl = snappy_compress((const uint8_t *)block.data(), nbytes, comp.data());
+      std::lock_guard<std::mutex> lk(file_mu_);
+      if (!failed_ && (fwrite(&cl, 8, 1, file_) != 1 || fwrite(comp.data(), 1, cl, file_) != cl)) { failed_ = true; err_ = "write to '" + name_ + "' failed"; }
+      n_olaps_ += m;
     }
   }
-  flushBlock();
 }
 
 bool OvFileWriter::close(std::string &err) {
-  if (th_.joinable()) {
+  if (!th_.empty()) {
     { std::lock_guard<std::mutex> lk(mu_); done_ = true; }
-    cv_.notify_one();
-    th_.join();
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+    th_.clear();
   }
   bool ok = !failed_;
   if (file_) { if (fclose(file_) != 0) ok = false; file_ = nullptr; }

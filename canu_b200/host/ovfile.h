@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -35,25 +36,26 @@ class OvFileWriter {
  public:
   OvFileWriter() {}
   ~OvFileWriter();
-  bool open(const std::string &name, uint32_t last_read_id, std::string &err);
+  bool open(const std::string &name, uint32_t last_read_id, std::string &err, unsigned n_threads = 1);
   void submit(std::vector<ovlb_record> &&batch);       // takes ownership; returns immediately
+  //  the same for a caller-owned (e.g. page-locked, recycled) buffer: `done` is called from a writer thread as soon as
+  //  the records have been consumed
+  void submit(const ovlb_record *recs, size_t n, std::function<void()> done);
   bool close(std::string &err);                         // drains, writes the .oc file
   uint64_t numOverlaps() const { return n_olaps_; }
 
  private:
   void run();
-  void flushBlock();
+  struct Batch { const ovlb_record *recs = nullptr; size_t n = 0; std::function<void()> done; };
 
   std::string name_, oc_name_;
   FILE *file_ = nullptr;
-  std::thread th_;
-  std::mutex mu_;
+  std::vector<std::thread> th_;
+  std::mutex mu_, file_mu_;
   std::condition_variable cv_;
-  std::deque<std::vector<ovlb_record>> q_;
+  std::deque<Batch> q_;
   bool done_ = false, failed_ = false;
   std::string err_;
-  std::vector<uint32_t> block_;         // words of the current block
-  std::vector<uint8_t> comp_;
   std::vector<uint32_t> opr_;
   uint64_t n_olaps_ = 0;
 };

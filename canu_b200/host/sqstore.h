@@ -43,6 +43,9 @@ class SqStore {
   uint32_t version()    const { return which_; }          // SQ_* flags of the default read version
   uint32_t libraryID(uint32_t id) const { return (uint32_t)((meta_[2 * (size_t)id] >> 30) & 0xfff); }
   uint32_t readLength(uint32_t id) const;                 // 0 if the read is not usable
+  uint32_t storedLength(uint32_t id) const {              // bases of the stored (uncompressed, untrimmed) sequence
+    return ((which_ & SQ_RAW) ? rawu_[id] : coru_[id]).length();
+  }
 
   //  The read as the overlapper sees it (default version: trimming / homopolymer compression applied),
   //  upper-case ASCII.  Returns false (and sets err) on a corrupt store.

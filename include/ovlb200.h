@@ -179,6 +179,12 @@ int  ovlb_overlap_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads,
  *  ovlb_fetch_records copies the records out.  */
 int  ovlb_stage_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads);
 int  ovlb_run_staged(ovlb_ctx *ctx, uint64_t *n_records);
+/*  Double buffering for a host that streams ref batches (Process_Overlaps' read loop, overlapInCore-Process_Overlaps.C:
+ *  25-122): ovlb_stage_next_ref_batch uploads and encodes batch i+1 into a SECOND slot on the copy stream -- call it
+ *  before ovlb_run_staged of batch i and the two overlap; ovlb_advance_staged then makes it the current batch (the
+ *  previous one is dropped).  The caller's buffers must stay valid until the batch has been run.  */
+int  ovlb_stage_next_ref_batch(ovlb_ctx *ctx, const ovlb_reads *reads);
+int  ovlb_advance_staged(ovlb_ctx *ctx);
 int  ovlb_fetch_records(ovlb_ctx *ctx, ovlb_record *out, uint64_t out_cap, uint64_t *n_out);   /* out: host OR device memory (UVA) */
 
 int  ovlb_get_counters(ovlb_ctx *ctx, ovlb_counters *out);
