@@ -138,6 +138,15 @@ def tiles_ours(args):
     json.dump(rows, open(os.path.join(args.outdir, "tiles_ours.json"), "w"), indent=1)
 
 
+def pick_threads(n_reads, cores):
+    """A -t for which the reference does not drop the last ref read."""
+    for t in range(cores, 0, -1):
+        per = 1 + (n_reads - 1) // t // 8
+        if (n_reads - 1) % per != 0:
+            return t
+    return 1
+
+
 def tiles_ref(args):
     make(args)
     st = os.path.join(args.store, "c3.seqStore")
@@ -145,8 +154,8 @@ def tiles_ref(args):
     rows = []
     for t in sampled_tiles(args):
         ovb = os.path.join(args.outdir, t["name"] + ".ref.ovb")
-        hb = sum(1 for _ in range(1))
-        cmd = [os.path.join(REF, "overlapInCore"), "-t", str(cores), "-k", "22", "--hashbits", "25", "--hashload", "0.8", "--hashdatalen", str(10 ** 10),
+        nthr = pick_threads(t["ref"][1] - t["ref"][0] + 1, cores)
+        cmd = [os.path.join(REF, "overlapInCore"), "-t", str(nthr), "-k", "22", "--hashbits", "25", "--hashload", "0.8", "--hashdatalen", str(10 ** 10),
                "--maxerate", ERATE, "--minlength", "500", "-h", "%d-%d" % t["hash"], "-r", "%d-%d" % t["ref"],
                "-o", ovb, "-s", os.path.join(args.outdir, t["name"] + ".ref.stats"), st]
         t0 = time.perf_counter()
@@ -156,7 +165,7 @@ def tiles_ref(args):
         c = subprocess.run([os.path.join(OURS, "ovltool"), "cmp-ovb", ovb, os.path.join(args.outdir, t["name"] + ".ours.ovb")], capture_output=True)
         so = open(os.path.join(args.outdir, t["name"] + ".ours.stats")).read()
         sr = open(os.path.join(args.outdir, t["name"] + ".ref.stats")).read()
-        rows.append(dict(t, ref_wall_s=round(wall, 1), ref_cores=cores, records_identical=c.returncode == 0,
+        rows.append(dict(t, ref_wall_s=round(wall, 1), ref_threads=nthr, records_identical=c.returncode == 0,
                          cmp=(c.stdout.decode().strip().splitlines() or ["?"])[-1], stats_identical=so == sr, stats=sr.splitlines()[:4]))
         print(json.dumps(rows[-1]), flush=True)
         os.remove(ovb)
@@ -175,7 +184,7 @@ def main():
     ap.add_argument("--hashblock", type=float, default=0)
     ap.add_argument("--out", default="")
     ap.add_argument("--tiles", type=int, default=2)
-    ap.add_argument("--tile-ref-reads", type=int, default=24)
+    ap.add_argument("--tile-ref-reads", type=int, default=66)
     ap.add_argument("--outdir", default="gpurun_out/c3tiles")
     args = ap.parse_args()
     {"make": make, "run": run, "tiles": tiles_ours, "reftiles": tiles_ref}[args.cmd](args)
