@@ -143,6 +143,7 @@ void ovlb_destroy(ovlb_ctx *c) {
 }
 
 int ovlb_load_hash_reads(ovlb_ctx *c, const ovlb_reads *reads) {
+  NvtxRange nvtx_("ovlb_load_hash_reads");
   if (!c || !reads) { ovl_set_error("ovlb_load_hash_reads: null argument"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   if (reads->n_reads >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
@@ -163,6 +164,7 @@ int ovlb_mark_skip_kmers(ovlb_ctx *c, const uint64_t *keys, uint64_t n) {
 }
 
 int ovlb_build_index(ovlb_ctx *c) {
+  NvtxRange nvtx_("ovlb_build_index");
   if (!c) { ovl_set_error("ovlb_build_index: null context"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   if (c->hash.fwd == nullptr && c->hash.n == 0 && c->hash.cap_reads == 0) { ovl_set_error("ovlb_build_index: no hash reads loaded"); return OVLB_ERR_STATE; }
@@ -170,6 +172,7 @@ int ovlb_build_index(ovlb_ctx *c) {
 }
 
 int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
+  NvtxRange nvtx_("ovlb_stage_ref_batch");
   if (!c || !reads) { ovl_set_error("ovlb_stage_ref_batch: null argument"); return OVLB_ERR_ARG; }
   if (reads->n_reads >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   CK(cudaSetDevice(c->device));
@@ -181,6 +184,7 @@ int ovlb_stage_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
 }
 
 int ovlb_stage_next_ref_batch(ovlb_ctx *c, const ovlb_reads *reads) {
+  NvtxRange nvtx_("ovlb_stage_next_ref_batch");
   if (!c || !reads) { ovl_set_error("ovlb_stage_next_ref_batch: null argument"); return OVLB_ERR_ARG; }
   if (reads->n_reads >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   if (c->staged_next) { ovl_set_error("ovlb_stage_next_ref_batch: a next batch is already staged; call ovlb_advance_staged first"); return OVLB_ERR_STATE; }
@@ -204,6 +208,7 @@ int ovlb_advance_staged(ovlb_ctx *c) {
 }
 
 int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
+  NvtxRange nvtx_("ovlb_run_staged");
   if (!c) { ovl_set_error("ovlb_run_staged: null context"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   if (!c->staged) { ovl_set_error("ovlb_run_staged: no staged ref batch"); return OVLB_ERR_STATE; }
@@ -224,8 +229,10 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
                           cudaStreamSynchronize(c->stream); memcpy(c->host_counters, hsnap, sizeof(hsnap)); };
   EvT tt(c->stream);
   c->n_records = 0;
-  int rc = ovl_seed_ref_batch(c);
+  int rc;
+  { NvtxRange r1("seed: probe + expand + sort + chain"); rc = ovl_seed_ref_batch(c); }
   if (rc) { tt.stop(); rollback(); return rc; }
+  NvtxRange r2("extend: k_extend_pairs");
   if (c->n_pairs) { rc = ovl_prepare_ext_scratch(c); if (rc) { tt.stop(); rollback(); return rc; } }   // allocation stays outside the kernel's bracket
   EvT te(c->stream);
   c->ext_warps_launched = 0;
@@ -250,6 +257,7 @@ int ovlb_run_staged(ovlb_ctx *c, uint64_t *n_records) {
 }
 
 int ovlb_fetch_records(ovlb_ctx *c, ovlb_record *out, uint64_t out_cap, uint64_t *n_out) {
+  NvtxRange nvtx_("ovlb_fetch_records");
   if (!c || !n_out) { ovl_set_error("ovlb_fetch_records: null argument"); return OVLB_ERR_ARG; }
   CK(cudaSetDevice(c->device));
   *n_out = c->n_records;

@@ -9,6 +9,11 @@
 #include "../../include/ovlb200.h"
 #include "ovl_common.cuh"
 
+//  NVTX ranges around the C-ABI stages (tracing): visible in Nsight Systems / Nsight Compute timelines;
+//  header-only NVTX v3, a no-op when no profiler is attached.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange { explicit NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+
 //  A set of reads resident in HBM (one for the hash block, one for the ref batch).
 struct DevReads {
   uint32_t  n = 0;

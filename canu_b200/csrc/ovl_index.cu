@@ -2017,6 +2017,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
 //  stats[0] distinct k-mers with count >= 2, [1] their total occurrences, [2] k-mers with count 1, [3] the threshold used.
 int ovl_kmer_census(ovlb_ctx *c, uint32_t slice_bits, double distinct_fraction, uint64_t min_count,
                     uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n_out, uint64_t stats[4]) {
+  NvtxRange nvtx_("ovlb_kmer_census");
   DevReads &H = c->hash;
   DevIndex &X = c->index;
   const int K = (int)c->P.kmer_len;

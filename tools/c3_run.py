@@ -111,7 +111,7 @@ def sampled_tiles(args):
     from canu_b200.host_util import store_read_lengths
     lens = store_read_lengths(os.path.join(args.store, "c3.seqStore"))
     tiles = api.plan_tiles(lens, 500, 160_000_000, 5_000_000_000, strict_reference=True)
-    pick = [tiles[int(i * (len(tiles) - 1) / max(args.tiles - 1, 1))] for i in range(args.tiles)] if len(tiles) > 1 else tiles
+    pick = [tiles[int((i + 0.5) * len(tiles) / args.tiles)] for i in range(args.tiles)] if len(tiles) > 1 else tiles
     out = []
     for k, t in enumerate(pick):
         span = t["ref_end"] - t["ref_bgn"] + 1
