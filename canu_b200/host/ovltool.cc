@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ovfile.h"
+#include "ovstore.h"
 #include "sqstore.h"
 
 using namespace ovlhost;
@@ -131,6 +132,16 @@ int main(int argc, char **argv) {
     printf("first %zu second %zu only-first %zu only-second %zu\n", A.size(), B.size(), onlyA, onlyB);
     return (onlyA || onlyB) ? 1 : 0;
   }
+  if (argc >= 5 && !strcmp(argv[1], "write-store")) {                  // flat SORTED {u32 a, u32 b, u64 dat0, u64 dat1} records -> ovStore directory
+    FILE *f = fopen(argv[2], "rb");
+    if (!f) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    std::vector<ovlb_record> recs; std::vector<ovlb_record> buf(1 << 20);
+    size_t got;
+    while ((got = fread(buf.data(), sizeof(ovlb_record), buf.size(), f)) > 0) recs.insert(recs.end(), buf.begin(), buf.begin() + got);
+    fclose(f);
+    if (!write_ovstore(argv[3], (uint32_t)strtoul(argv[4], nullptr, 10), recs.data(), recs.size(), err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    return 0;
+  }
   if (argc >= 3 && !strcmp(argv[1], "lengths")) {                      // read lengths as the overlapper sees them, one per line (ID order)
     SqStore S;
     if (!S.open(argv[2], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
@@ -149,6 +160,6 @@ int main(int argc, char **argv) {
     printf("%zu:%016lx%016lx\n", recs.size(), (unsigned long)s1, (unsigned long)s2);
     return 0;
   }
-  fprintf(stderr, "usage: ovltool lengths <seqStore> | hash-ovb <file.ovb> | dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
+  fprintf(stderr, "usage: ovltool write-store <sorted.bin> <out.ovlStore> <lastReadID> | lengths <seqStore> | hash-ovb <file.ovb> | dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
   return 1;
 }
