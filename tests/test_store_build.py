@@ -63,7 +63,7 @@ def test_written_store_reads_back_like_the_reference_store(tmp_path, erate):
     subprocess.check_call([os.path.join(OURS, "ovltool"), "write-store", flat, ours, str(n_reads)])
     assert open(os.path.join(ours, "info"), "rb").read() == open(os.path.join(ref, "info"), "rb").read()
     assert open(os.path.join(ours, "0001-001"), "rb").read() == open(os.path.join(ref, "0001-001"), "rb").read()
-    for w in WHAT:
+    for w in (WHAT if erate else WHAT[1:]):                 # the full text dump once: the reference tool takes its time
         a, b = _dump(ours, seq, w), _dump(ref, seq, w)
         assert a == b and len(a) > 100, w
 
