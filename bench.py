@@ -523,9 +523,9 @@ def main():
         # brackets on the library's stream around each kernel (group) of the step; a stage of n identical launches
         # is divided by n: `achieved` is algorithmic bytes PER LAUNCH over time PER LAUNCH.
         stage_def = {   # stage: (kernel, launches, algorithmic bytes per launch)
-            "index_tuples_ms": ("k_hash_tuples_compact", 1, hk * (0.5 + 12)),
-            "index_sort_ms": ("radix partition over the bucket bits (per pass)", 2, hk * 12 * 2),
-            "index_table_ms": ("k_bucket_group + path sort + k_path_slots", 1, hk * (12 + 4)),
+            "index_tuples_ms": ("k_part1 (k-mers -> tuples scattered into coarse partitions)", 1, hk * (0.5 + 16)),
+            "index_sort_ms": ("k_part2 (coarse partition -> buckets, 8-byte tuples)", 1, hk * (16 + 8)),
+            "index_table_ms": ("k_bucket_group2 (bulk-copy fed) + first-position bitmap + k_path_slots2", 1, hk * (8 + 4)),
             "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),
             "expand_ms": ("k_expand_small + k_expand_large", 1, sr * (4 + 16 + 16)),
             "sort_ms": ("radix sort of the seed runs", 8, sr * 16 * 2),

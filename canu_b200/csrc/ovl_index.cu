@@ -1874,6 +1874,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
     uint64_t want = c->mem_budget / 12 / 88;               // ~1/12 of the budget over 88 B/run of run-side arrays
     if (want < (1u << 20)) want = 1u << 20;
     if (want > (1ull << 31)) want = 1ull << 31;
+    if (const char *ev = getenv("OVLB_RUN_CAP")) { const long long v = atoll(ev); if (v > 0) want = (uint64_t)v; }   // tests: force the overflow path
     size_t cap0 = 0, cap1 = 0, cap2 = 0, cap3 = 0, cap4 = 0, cap5 = 0;
     if ((rc = ensure(c->run_key, cap0, want, 1, 1))) return rc;
     if ((rc = ensure(c->run_val, cap1, want, 1, 1))) return rc;

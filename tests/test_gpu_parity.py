@@ -432,3 +432,46 @@ def test_reads_prepared_on_the_device_match_reads_prepared_on_the_host(homopoly)
     assert len(out[0][0]) > 300
     assert out[0][0].tobytes() == out[1][0].tobytes()
     assert out[0][1] == out[1][1]
+
+
+def test_seed_buffer_overflow_is_split_and_counted_once(tmp_path):
+    """A ref batch that overflows the device's seed buffers fails with OVLB_ERR_CAPACITY; the executable cuts it in two
+    and re-queues the halves (several levels deep here: OVLB_RUN_CAP forces a tiny buffer).  Records, .oc and -- because a
+    failed run rolls its partial counters back -- the .stats file must still be the reference's golden output."""
+    import os
+    import subprocess
+    api = _api()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "canu_b200", "bin", "overlapInCore")
+    tool = os.path.join(root, "canu_b200", "bin", "ovltool")
+    c = gu.get_case("A_default")
+    store = os.path.join(gu.GOLDEN, "A.seqStore")
+    ovb = str(tmp_path / "out.ovb")
+    cmd = [exe, "-k", "22", "--minlength", "500"] + c["flags"] + ["-h", "1-220", "-r", "1-220", "-o", ovb, "-s", str(tmp_path / "out.stats"), store]
+    r = subprocess.run(cmd, capture_output=True, env=dict(os.environ, OVLB_RUN_CAP="6000"))
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert r.stderr.decode().count("Processed reads") >= 4            # the one planned batch really was split
+    lines = subprocess.check_output([tool, "dump-ovb", ovb]).decode().splitlines()
+    recs = np.zeros(len(lines), dtype=[("a_iid", "<u4"), ("b_iid", "<u4"), ("w0", "<u8"), ("w1", "<u8")])
+    for i, ln in enumerate(lines):
+        x = ln.split()
+        recs[i] = (int(x[0]), int(x[1]), int(x[2], 16), int(x[3], 16))
+    got, want = gu.format_records(recs), gu.load_golden_lines("A_default")
+    assert got == want, _diff_msg(got, want)
+    assert open(str(tmp_path / "out.stats")).read() == open(os.path.join(gu.GOLDEN, "A_default.stats")).read()
+    assert open(str(tmp_path / "out.oc"), "rb").read() == open(os.path.join(gu.GOLDEN, "A_default.oc"), "rb").read()
+    # through the C ABI: the error code, then the same batch in halves gives the whole result
+    os.environ["OVLB_RUN_CAP"] = "6000"
+    try:
+        reads = gu.load_dump_reads("A")
+        prm = api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500, max_read_len=max(r.size for r in reads))
+        ov = api.Overlapper(prm)
+        pk = api.PackedReads(reads, first_read_id=1, min_len=500)
+        ov.load_hash_reads(pk); ov.build_index(); ov.stage_ref_batch(pk)
+        with pytest.raises(api.OvlError) as ei:
+            ov.run_staged()
+        assert ei.value.code == -3
+        assert ov.counters()["pairs"] == 0 and ov.counters()["kmer_hits_with_olap"] == 0      # rolled back
+        ov.close()
+    finally:
+        del os.environ["OVLB_RUN_CAP"]
