@@ -1372,6 +1372,133 @@ k_expand_large(ExpandArgs A, const uint4 *__restrict__ items, const unsigned lon
   if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
 }
 
+//  Round 2: one cooperative kernel for all items.  The thread-per-item / warp-per-item kernels above ran with 6-7 of 32
+//  lanes active (ncu: thread_inst_executed_per_inst 6.2 / 7.5): on HiFi-like reads a run is hundreds of hits long and
+//  every lane walked its own 16-bases-per-step comparison loop for a different number of steps.  Here a warp takes 32
+//  items, expands them into (item, occurrence) candidates by a prefix sum (load-balanced: 32 candidates at a time
+//  whatever the item sizes), filters them in parallel (refID < hashID, all metadata loads independent), and then
+//  measures each surviving run with the WHOLE warp: 512 bases per step, like the extension kernel's slide.
+struct ExpCand { const uint64_t *rw, *hw; int p, q, lim; uint32_t pos_dir; uint32_t r, hh; };   // 40 bytes
+
+__global__ void __launch_bounds__(256)
+k_expand_coop(ExpandArgs A, const uint4 *__restrict__ items_small, const unsigned long long *n_small_p,
+              const uint4 *__restrict__ items_large, const unsigned long long *n_large_p, uint64_t item_cap,
+              unsigned long long *counters) {
+  __shared__ uint64_t st_key[8][RUN_STAGE], st_val[8][RUN_STAGE];
+  __shared__ ExpCand cand[8][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  RunStage S; S.key = st_key[wib]; S.val = st_val[wib]; S.n = 0;
+  ExpCand *C = cand[wib];
+  unsigned long long n_small = *n_small_p, n_large = *n_large_p;
+  if (n_small > item_cap) n_small = item_cap;
+  if (n_large > item_cap) n_large = item_cap;
+  const unsigned long long n_items = n_small + n_large;
+  unsigned long long hits = 0;
+  const uint64_t wstride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t i0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < n_items; i0 += wstride * 32) {
+    const uint64_t i = i0 + lane;
+    uint4 it = make_uint4(0, 0, 0, 0);
+    if (i < n_items) it = i < n_small ? items_small[i] : items_large[i - n_small];
+    const uint32_t cnt = it.z >> 1;
+    //  per item (ref side): read, offset in the read, its words
+    uint32_t r = 0; uint64_t rp = 0, rwo = 0; int rL = 0;
+    if (cnt) { r = A.rgrp_read[it.x >> 5]; rp = A.rpbase[r]; rL = (int)A.rlen[r]; rwo = A.rwoff[r]; }
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+    const uint32_t excl = incl - cnt;
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t cb = 0; cb < total; cb += 32) {
+      const uint32_t c = cb + lane;
+      const bool active = c < total;
+      //  owner item of candidate c: the largest l with excl_l <= c
+      int l = 0;
+      #pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int probe = l + step;
+        const uint32_t v = __shfl_sync(0xffffffffu, excl, probe & 31);
+        if (probe < 32 && v <= c) l = probe;
+      }
+      const uint32_t j = c - __shfl_sync(0xffffffffu, excl, l);
+      const uint32_t pos_l = __shfl_sync(0xffffffffu, it.x, l), y_l = __shfl_sync(0xffffffffu, it.y, l), z_l = __shfl_sync(0xffffffffu, it.z, l);
+      const uint32_t r_l = __shfl_sync(0xffffffffu, r, l);
+      const uint64_t rp_l = __shfl_sync(0xffffffffu, rp, l), rwo_l = __shfl_sync(0xffffffffu, rwo, l);
+      const int rL_l = __shfl_sync(0xffffffffu, rL, l);
+      bool pass = false;
+      if (active) {
+        const uint32_t hpos = A.occ[y_l + j];
+        const uint32_t hh = A.hgrp_read[hpos >> 5];
+        if (A.ref_first_id + r_l < A.hash_first_id + hh) {                // only refID < hashID pairs (Find_Overlaps.C:279,320)
+          pass = true;
+          const int dir = (int)(z_l & 1u);
+          ExpCand e;
+          e.p = (int)(pos_l - rp_l);
+          e.q = (int)(hpos - A.hpbase[hh]);
+          e.lim = min(rL_l - (e.p + A.K), (int)A.hlen[hh] - (e.q + A.K));
+          e.rw = (dir ? A.rrc : A.rfwd) + rwo_l;
+          e.hw = A.hfwd + A.hwoff[hh];
+          e.pos_dir = pos_l; e.r = (r_l << 1) | (uint32_t)dir; e.hh = hh;
+          C[lane] = e;
+          //  the survivors are measured one after the other by the whole warp: have their first lines on the way
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(e.rw + ((e.p + A.K) >> 4)));
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(e.hw + ((e.q + A.K) >> 4)));
+          asm volatile("prefetch.global.L1 [%0];" :: "l"(A.ref_valid + (((uint64_t)dir * A.r_npos + pos_l) >> 5)));
+        }
+      }
+      __syncwarp();
+      for (unsigned surv = __ballot_sync(0xffffffffu, pass); surv; surv &= surv - 1) {
+        const ExpCand e = C[__ffs(surv) - 1];
+        const int dir = (int)(e.r & 1u);
+        //  run length: equal bases after the k-mer, 512 per step ...
+        int e2 = 0;
+        while (e2 < e.lim) {
+          const int off = e2 + 16 * lane;
+          int k = 16;
+          if (off < e.lim) k = ovl_equal16(ovl_fetch16(e.rw, e.p + A.K + off), ovl_fetch16(e.hw, e.q + A.K + off));
+          const unsigned nf = __ballot_sync(0xffffffffu, k < 16);
+          if (nf == 0) { e2 += 512; continue; }
+          const int first = __ffs(nf) - 1;
+          e2 += 16 * first + __shfl_sync(0xffffffffu, k, first);
+          break;
+        }
+        if (e2 > e.lim) e2 = e.lim;
+        const int want = e2 + 1;
+        //  ... and consecutive hit windows on the ref side (a skip k-mer or an N ends the run)
+        const uint64_t vbase = (uint64_t)dir * A.r_npos;
+        uint64_t wi = (vbase + e.pos_dir) >> 5;
+        const int b = (int)(e.pos_dir & 31);
+        const uint32_t rem = A.ref_valid[wi] >> b;
+        int nv = __ffs(~rem) - 1;
+        if (nv < 0 || nv > 32 - b) nv = 32 - b;
+        if (nv == 32 - b) {
+          wi++;
+          while (nv < want) {
+            const uint32_t x = A.ref_valid[wi + lane];
+            const unsigned part = __ballot_sync(0xffffffffu, x != 0xFFFFFFFFu);
+            if (part == 0) { nv += 1024; wi += 32; continue; }
+            const int f = __ffs(part) - 1;
+            const uint32_t xf = __shfl_sync(0xffffffffu, x, f);
+            nv += 32 * f + (__ffs(~xf) - 1);
+            break;
+          }
+        }
+        const uint32_t runlen = (uint32_t)min(want, nv);
+        if (lane == 0) {
+          S.key[S.n] = ovl_runkey(e.r >> 1, (uint32_t)dir, e.hh, (uint32_t)e.p);
+          S.val[S.n] = (uint64_t)(uint32_t)e.q | ((uint64_t)runlen << 32);
+          hits += runlen;
+        }
+        S.n++;
+        if (S.n == RUN_STAGE) { __syncwarp(); run_flush(A, S, lane); }
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  run_flush(A, S, lane);
+  if (lane == 0 && hits) atomicAdd(&counters[CT_SEED_HITS], hits);
+}
+
 // ------------------------------------------------------------------------------------------------
 //  K3: pairs and seed lists
 // ------------------------------------------------------------------------------------------------
@@ -1866,7 +1993,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
   if (R.n >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   if (H.n >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); split it"); return OVLB_ERR_CAPACITY; }
 
-  if ((rc = ensure(c->ref_valid, c->ref_valid_cap, (size_t)2 * n_groups + 8))) return rc;
+  if ((rc = ensure(c->ref_valid, c->ref_valid_cap, (size_t)2 * n_groups + 80))) return rc;
   if ((rc = ensure_groups(c, R))) return rc;
 
   //  run and item buffers: sized from the memory budget once; overflow -> OVLB_ERR_CAPACITY
@@ -1887,7 +2014,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
 
   CK(cudaMemsetAsync(c->d_work, 0, 40, c->stream));       // [0] n_runs, [1] extend work cursor, [2] n_records, [3] small items, [4] large items
   CK(cudaMemsetAsync(R.flags, 0, (size_t)(R.n + 1) * 8, c->stream));
-  CK(cudaMemsetAsync(c->ref_valid + 2 * n_groups, 0, 32, c->stream));     // the run-length scan may peek one word past the end
+  CK(cudaMemsetAsync(c->ref_valid + 2 * n_groups, 0, 72 * 4, c->stream));  // the run-length scan peeks up to 32 words past the word it needs
 
   EvTimer t1(c->stream);
   if (n_groups) {
@@ -1912,9 +2039,15 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
     A.K = K; A.occ = X.occ; A.ref_valid = c->ref_valid;
     A.run_key = c->run_key; A.run_val = c->run_val; A.run_cap = c->run_cap; A.n_runs = &c->d_work[0];
     const int grid = c->sm_count * 8;
-    k_expand_large<<<grid, 256, 0, c->stream>>>(A, c->item_large, &c->d_work[4], c->run_cap, c->d_counters->v);
-    k_expand_small<<<grid, 256, 0, c->stream>>>(A, c->item_small, &c->d_work[3], c->run_cap, c->d_counters->v);
-    c->launches += 2;
+    static const int old_expand = [] { const char *ev = getenv("OVLB_EXPAND_OLD"); return ev ? atoi(ev) : 0; }();
+    if (old_expand) {
+      k_expand_large<<<grid, 256, 0, c->stream>>>(A, c->item_large, &c->d_work[4], c->run_cap, c->d_counters->v);
+      k_expand_small<<<grid, 256, 0, c->stream>>>(A, c->item_small, &c->d_work[3], c->run_cap, c->d_counters->v);
+      c->launches += 2;
+    } else {
+      k_expand_coop<<<grid, 256, 0, c->stream>>>(A, c->item_small, &c->d_work[3], c->item_large, &c->d_work[4], c->run_cap, c->d_counters->v);
+      c->launches++;
+    }
   }
   CK(cudaGetLastError());
   unsigned long long w5[5] = {0, 0, 0, 0, 0};
