@@ -543,7 +543,7 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and args.hifi_genome == 5_000_000 and args.hifi_coverage == 50.0:
-            traffic = json.load(open(tpath)).get(dom + "_ms")
+            traffic = json.load(open(tpath)).get(dom)
         index_ms = hst.get("index_tuples_ms", 0) + hst.get("index_sort_ms", 0) + hst.get("index_table_ms", 0)
         roofline = {"bound": "hbm", "kernel": stage_roof[dom]["kernel"], "stage": dom, "achieved": stage_roof[dom]["achieved"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic, "peak_source": which,
