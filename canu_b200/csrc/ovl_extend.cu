@@ -26,7 +26,7 @@
 
 #define EXT_WARPS  8
 #define EXT_THREADS (EXT_WARPS * 32)
-#define SRING      512                    // ints per shared ring (per row, per warp)
+#define SRING      256                    // ints per shared ring (per row, per warp)
 #define SRING_PAD  64                     // slack behind every ring: the branch-free cell front reads predecessors of masked lanes
 #define SRING_STRIDE (SRING + SRING_PAD)
 #define FULL       0xffffffffu
