@@ -475,3 +475,38 @@ def test_seed_buffer_overflow_is_split_and_counted_once(tmp_path):
         ov.close()
     finally:
         del os.environ["OVLB_RUN_CAP"]
+
+
+def test_midsize_job_against_the_live_reference_binary(tmp_path):
+    """Driver-visible bench-scale parity: a mid-size job (0.25 Mbp x 30x, 2-8 kb reads, 1.5 % error, --maxerate 0.045:
+    ~10 s for the reference on the box's cores) through the REFERENCE binary and through the drop-in executable on the
+    same reference-made sqStore: canonically sorted records, .stats and .oc identical."""
+    import os
+    import subprocess
+    from canu_b200 import synth
+    _api()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref", "bin")
+    if not os.path.exists(os.path.join(ref, "overlapInCore")):
+        pytest.skip("oracle/_ref not built")
+    ours = os.path.join(root, "canu_b200", "bin")
+    g = synth.make_genome(250000, seed=77)
+    reads = synth.simulate_reads(g, 30, 2000, 8000, 0.015, seed=78)
+    fa, st = str(tmp_path / "r.fasta"), str(tmp_path / "r.seqStore")
+    synth.write_fasta(fa, reads)
+    subprocess.check_call([os.path.join(ref, "sqStoreCreate"), "-o", st, "-minlength", "1000", "-pacbio", "lib", fa],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    n = len(reads)
+    cores = os.cpu_count() or 1
+    t = next(t for t in range(cores, 0, -1) if (n - 1) % (1 + (n - 1) // t // 8) != 0)     # no last-ref-read drop (SURVEY 7.5a)
+    common = ["-k", "22", "--hashbits", "22", "--hashload", "0.8", "--hashdatalen", str(10 ** 10), "--maxerate", "0.045",
+              "--minlength", "500", "-h", "1-%d" % n, "-r", "1-%d" % n]
+    for who, exe in (("ref", os.path.join(ref, "overlapInCore")), ("our", os.path.join(ours, "overlapInCore"))):
+        r = subprocess.run([exe, "-t", str(t)] + common + ["-o", str(tmp_path / (who + ".ovb")), "-s", str(tmp_path / (who + ".stats")), st],
+                           capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()[-1500:]
+    c = subprocess.run([os.path.join(ours, "ovltool"), "cmp-ovb", str(tmp_path / "ref.ovb"), str(tmp_path / "our.ovb")], capture_output=True)
+    assert c.returncode == 0, c.stdout.decode()[-600:]
+    assert int(c.stdout.decode().split()[-7]) > 20000                                       # "first N second N ..."
+    assert open(str(tmp_path / "ref.stats")).read() == open(str(tmp_path / "our.stats")).read()
+    assert open(str(tmp_path / "ref.oc"), "rb").read() == open(str(tmp_path / "our.oc"), "rb").read()
