@@ -31,7 +31,7 @@ records on rank 0 (the reference's "merged on the host"), inside the timed regio
   records_sha256  hash of the canonically sorted records of the whole job: equal at every N.
   cpu_baseline / --impl reference: the UNMODIFIED reference overlapInCore (oracle/_ref, built by oracle/build_ref.sh),
          -t <all host cores>, on that same sample.
-  hifi_tile (rank 0, N=1): the C2 tile of BASELINE.json configs[1] (5 Mbp x 50x HiFi-like, --maxerate 0.01), where the
+  hifi_tile (rank 0): the C2 tile of BASELINE.json configs[1] (5 Mbp x 50x HiFi-like, --maxerate 0.01), where the
          index build and the lookup are a large share of the step: per-stage HBM rooflines; `roofline` is its longest
          HBM-bound launch.  The job's own dominant kernel, k_extend_pairs, is integer-ALU / issue bound (no GEMM shape,
          no tensor cores): reported under `extension` as DP Gcell/s with the warp-busy fraction of the launch.
@@ -495,7 +495,7 @@ def main():
 
     # ---- secondary: the C2 tile (HiFi-like reads), where index build and lookup matter: per-stage HBM rooflines
     roofline = None
-    if world == 1 and args.hifi_genome > 0:
+    if args.hifi_genome > 0:                         # rank 0, every N: the other ranks wait at the final barrier
         hreads = make_hifi_tile(args.hifi_genome, args.hifi_coverage, seed=2001)
         hprm = api.OverlapParams(kmer_len=K, max_erate=HIFI_ERATE, min_olap_len=MINLEN, max_read_len=max(r.size for r in hreads))
         hov = api.Overlapper(hprm, device=local_rank)

@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 REF = os.path.join(ROOT, "oracle", "_ref", "bin")
 OURS = os.path.join(ROOT, "canu_b200", "bin")
 READ_ERR, ERATE, LEN_LO, LEN_HI = 0.03, "0.06", 10000, 20000
+if os.environ.get("C3RUN_MODEL") == "C1":          # BASELINE configs[0] read model through the same tooling (pass --genome 4.6e6 --coverage 30)
+    READ_ERR, ERATE, LEN_LO, LEN_HI = 0.01, "0.045", 3000, 15000
 
 _G = None
 
