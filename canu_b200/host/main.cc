@@ -383,7 +383,10 @@ int main(int argc, char **argv) {
   if (W > 1 && !tiles.empty()) {
     std::vector<std::pair<uint32_t, uint32_t>> blocks;
     for (const ovlb_tile &T : tiles) if (blocks.empty() || blocks.back().first != T.hash_bgn) blocks.push_back({T.hash_bgn, T.hash_end});
-    if (blocks.size() < 2 * (size_t)W) {
+    //  noisy reads: the index build is < 1 % of a tile, so balanced parts win until there are many blocks per GPU (C3 on two
+    //  GPUs with 9 whole blocks dealt out: 197.7 s against 176.9 s of extension); HiFi-like reads: the build is a quarter
+    const size_t wholeBlocksFrom = (G.maxErate >= 0.03 ? 16 : 2) * (size_t)W;
+    if (blocks.size() < wholeBlocksFrom) {
       const double lookupWeight = G.maxErate >= 0.03 ? 0.01 : 0.6;
       const uint64_t maxPiece = G.refBatchBases ? G.refBatchBases : 256000000ull;
       std::vector<ovlb_tile> bal;
