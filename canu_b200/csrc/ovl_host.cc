@@ -198,55 +198,54 @@ int ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ola
                     int strict_reference, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out) {
   if (!read_len || !n_out) { ovl_set_error("ovlb_plan_tiles: null argument"); return OVLB_ERR_ARG; }
   if (hash_block_len == 0 || ref_block_len == 0) { ovl_set_error("ovlb_plan_tiles: block lengths must be positive"); return OVLB_ERR_ARG; }
-  if (hash_min < 1) hash_min = 1;
-  if (ref_min < 1) ref_min = 1;
-  if (hash_max > n_reads) hash_max = n_reads;
-  if (ref_max > n_reads) ref_max = n_reads;
-  const uint32_t lastStartAdj = strict_reference ? 0 : 1;       // reference: strictly below the max; ours: up to it
-  uint64_t totalHashable = 0;
-  for (uint32_t id = hash_min; id <= hash_max; id++) if (read_len[id] >= min_olap_len) totalHashable += (uint64_t)read_len[id] + 1;
-  uint64_t n = 0;
-  uint32_t hashBeg = hash_min, hashEnd = hash_min - 1;
-  while (hashBeg < hash_max + lastStartAdj) {
-    uint64_t hashLen = 0, hashBases = 0; uint32_t hashReads = 0;
-    do {
-      hashEnd++;
-      if (read_len[hashEnd] < min_olap_len) continue;
-      hashLen += (uint64_t)read_len[hashEnd] + 1;
-      hashReads += 1;
-      hashBases += (uint64_t)read_len[hashEnd] + 1;
-    } while (hashLen < hash_block_len && hashEnd < hash_max);
+  hash_min = std::max(hash_min, 1u); ref_min = std::max(ref_min, 1u);
+  hash_max = std::min(hash_max, n_reads); ref_max = std::min(ref_max, n_reads);
+  //  a read counts for a block only if it is long enough to be overlapped; a hashed read also costs its terminator
+  auto usable = [&](uint32_t id) -> uint64_t { return read_len[id] >= min_olap_len ? (uint64_t)read_len[id] : 0; };
+  auto hashed = [&](uint32_t id) -> uint64_t { return read_len[id] >= min_olap_len ? (uint64_t)read_len[id] + 1 : 0; };
+  //  the reference's loops only START a block on a read strictly below the range's last one (so its last read can be
+  //  left out of the grid); with strict_reference == 0 every read of the range is covered
+  const uint32_t start_slack = strict_reference ? 0u : 1u;
+  uint64_t all_hashed = 0;
+  for (uint32_t id = hash_min; id <= hash_max; id++) all_hashed += hashed(id);
 
-    uint32_t refBeg = ref_min, refEnd = 0;
-    if (!strict_reference) refEnd = ref_min - 1;
-    while (refBeg < ref_max + lastStartAdj && refBeg < hashEnd) {
-      uint64_t refLen = 0, refBases = 0;
-      do {
-        refEnd++;
-        if (read_len[refEnd] < min_olap_len) continue;
-        refLen += read_len[refEnd];
-        refBases += (uint64_t)read_len[refEnd] + 1;
-      } while (refLen < ref_block_len && refEnd < ref_max);
-      if (refEnd > ref_max) refEnd = ref_max;
-      if (refEnd > hashEnd) refEnd = hashEnd;
-      if (out && n < out_cap) {
-        ovlb_tile &t = out[n];
-        t.hash_bgn = hashBeg; t.hash_end = hashEnd; t.ref_bgn = refBeg; t.ref_end = refEnd;
-        uint64_t rb = 0;                                 // ref bases actually inside the (clamped) block
-        for (uint32_t id = refBeg; id <= refEnd; id++) if (read_len[id] >= min_olap_len) rb += read_len[id];
-        t.hash_bases = hashBases; t.ref_bases = rb;
+  uint64_t made = 0;
+  for (uint32_t h_first = hash_min; h_first < hash_max + start_slack; ) {
+    //  grow the hash block read by read until it holds hash_block_len bases (+ terminators) or the range ends
+    uint32_t h_last = h_first - 1, n_hashed = 0;
+    uint64_t h_size = 0;
+    while (true) {
+      h_last++;
+      const uint64_t add = hashed(h_last);
+      h_size += add; n_hashed += add != 0;
+      if (h_size >= hash_block_len || h_last >= hash_max) break;
+    }
+    //  cross it with ref blocks; a ref block never reaches past the hash block's last read (refID < hashID)
+    uint32_t r_last = strict_reference ? 0u : ref_min - 1;
+    for (uint32_t r_first = ref_min; r_first < ref_max + start_slack && r_first < h_last; r_first = r_last + 1) {
+      uint64_t r_size = 0;
+      while (true) {
+        r_last++;
+        r_size += usable(r_last);
+        if (r_size >= ref_block_len || r_last >= ref_max) break;
+      }
+      r_last = std::min(r_last, std::min(ref_max, h_last));
+      if (out && made < out_cap) {
+        ovlb_tile &t = out[made];
+        t.hash_bgn = h_first; t.hash_end = h_last; t.ref_bgn = r_first; t.ref_end = r_last;
+        t.hash_bases = h_size; t.ref_bases = 0;
+        for (uint32_t id = r_first; id <= r_last; id++) t.ref_bases += usable(id);     // bases actually inside the clamped block
         //  cost model: index build ~ hash bases; lookup ~ 2 orientations of the ref bases; extension ~ ref bases
         //  x the share of all hashable reads that sit in this hash block (= share of each read's overlaps found here)
-        t.cost = (double)hashBases + (double)rb * (2.0 + 8.0 * (double)hashBases / (double)(totalHashable ? totalHashable : 1));
-        t.has_hash_reads = hashReads != 0;
+        t.cost = (double)h_size + (double)t.ref_bases * (2.0 + 8.0 * (double)h_size / (double)(all_hashed ? all_hashed : 1));
+        t.has_hash_reads = n_hashed != 0;
       }
-      n++;
-      refBeg = refEnd + 1;
+      made++;
     }
-    hashBeg = hashEnd + 1;
+    h_first = h_last + 1;
   }
-  *n_out = n;
-  if (out && n > out_cap) { ovl_set_error("ovlb_plan_tiles: output buffer too small"); return OVLB_ERR_CAPACITY; }
+  *n_out = made;
+  if (out && made > out_cap) { ovl_set_error("ovlb_plan_tiles: output buffer too small"); return OVLB_ERR_CAPACITY; }
   return OVLB_OK;
 }
 
