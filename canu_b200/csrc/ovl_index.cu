@@ -1128,12 +1128,12 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
             uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint32_t n_slots,
             const HashEntry *__restrict__ ht, uint64_t hcap,
             uint32_t *__restrict__ ref_valid, uint32_t *rflags,
-            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work) {
+            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work, bool one_list) {
   __shared__ uint4 stage[WARPS_PER_BLOCK][STAGE_SMALL + STAGE_LARGE];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   ItemStage SS, SL;
-  SS.buf = stage[wib];               SS.n = 0; SS.cap = STAGE_SMALL; SS.out = item_small; SS.counter = &work[3]; SS.out_cap = item_cap;
+  SS.buf = stage[wib];               SS.n = 0; SS.cap = one_list ? STAGE_SMALL + STAGE_LARGE : STAGE_SMALL; SS.out = item_small; SS.counter = &work[3]; SS.out_cap = item_cap;
   SL.buf = stage[wib] + STAGE_SMALL; SL.n = 0; SL.cap = STAGE_LARGE; SL.out = item_large; SL.counter = &work[4]; SL.out_cap = item_cap;
 
   const uint64_t total = 2 * n_groups;
@@ -1222,10 +1222,15 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       }
       if (__any_sync(0xffffffffu, n0 | n1)) {
         const uint32_t pos = (uint32_t)(g * 32 + lane);
-        stage_append(SS, n0 > 0 && n0 <= SMALL_ITEM_MAX, make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
-        stage_append(SL, n0 > SMALL_ITEM_MAX,            make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
-        stage_append(SS, n1 > 0 && n1 <= SMALL_ITEM_MAX, make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
-        stage_append(SL, n1 > SMALL_ITEM_MAX,            make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+        if (one_list) {                                  // the cooperative expand kernel takes items of any size from one list
+          stage_append(SS, n0 > 0, make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
+          stage_append(SS, n1 > 0, make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+        } else {
+          stage_append(SS, n0 > 0 && n0 <= SMALL_ITEM_MAX, make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
+          stage_append(SL, n0 > SMALL_ITEM_MAX,            make_uint4(pos, b0, (n0 << 1) | (uint32_t)dir, 0), lane);
+          stage_append(SS, n1 > 0 && n1 <= SMALL_ITEM_MAX, make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+          stage_append(SL, n1 > SMALL_ITEM_MAX,            make_uint4(pos, b1, (n1 << 1) | (uint32_t)dir, 0), lane);
+        }
       }
     }
   }
@@ -2023,7 +2028,7 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
     if (per_sm < 1) per_sm = 1;
     k_ref_probe<<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
         R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.n_slots, X.htab, X.hcap,
-        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work);
+        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work, getenv("OVLB_EXPAND_OLD") == nullptr);
     c->launches++;
   }
   CK(cudaGetLastError());

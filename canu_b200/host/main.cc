@@ -523,11 +523,14 @@ int main(int argc, char **argv) {
     auto take = [&](Staged &S, std::string &err) -> bool {                // next batch of the queue, packed and pinned
       const Work w = q.front(); q.pop_front();
       double t1 = now_s();
+      //  page-locking pays where uploads are a visible share of a tile (HiFi-like reads: 33 ms tiles); a noisy tile runs for
+      //  seconds and a registration costs tens of milliseconds (C3 on 4 GPUs: 3.1 s of `stage` for nothing)
+      static const bool pinBatches = G.maxErate < 0.03;
       if (w.planned) { S.own = pf.next(err); if (!S.own) return false; }
       else { S.own = pf.spare(); if (!pack_range(st, w.rb, w.re, G.minLibToRef, G.maxLibToRef, minLen, *S.own, err)) return false; }
       S.rb = w.rb; S.re = w.re;
       ph.pack_ref += now_s() - t1; t1 = now_s();
-      pin(*S.own);
+      if (pinBatches) pin(*S.own);
       ph.stage += now_s() - t1;
       return true;
     };
