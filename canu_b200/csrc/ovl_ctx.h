@@ -43,7 +43,7 @@ struct DevReads {
 //  (the reference's Empty flag).
 #define OVL_SKIP_BIT (1ull << 63)
 struct __align__(32) IndexSlot { uint64_t key; uint32_t start; uint32_t end[5]; };
-struct __align__(16) HashEntry { uint64_t key; uint32_t idx; uint32_t pad; };
+struct __align__(8) HashEntry { uint32_t idx; uint32_t fp; };      // one 64-bit word: fingerprint << 32 | slot index; buckets of four
 
 struct DevIndex {
   uint32_t   n_slots = 0;         // slots in use: distinct k-mers + skip k-mers no hash read holds

@@ -366,42 +366,62 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
 //  wherever that read -- or any read covering the same stretch without an error -- was the first to bring those
 //  k-mers in, so the lookup of 32 consecutive ref windows is normally ONE 1 KB coalesced load (8 lines) instead of
 //  32 random probes that cost a 128-byte line each (tools/micro/rand_sector.cu: 36.9 G random lines/s is all B200
-//  gives, whatever the load width).  `htab` (open addressing, 16-byte entries: k-mer, slot index) is only consulted
-//  where the path breaks: a read start, an error, the border between two first-coverage stretches.
+//  gives, whatever the load width).  `htab` (below) is only consulted where the path breaks: a read start, an error, the
+//  border between two first-coverage stretches -- and for every window whose k-mer is not in the block at all.
 //  ------------------------------------------------------------------------------------------------
 #define HT_EMPTY   0xFFFFFFFFFFFFFFFFull
 #define HT_NOTFOUND 0xFFFFFFFFu
+#define HT_MULT    0x9E3779B97F4A7C15ull
 
-__device__ __forceinline__ uint64_t ht_home(uint64_t key, uint64_t hcap) { return __umul64hi(key * 0x9E3779B97F4A7C15ull, hcap); }
+//  `htab`: buckets of four 8-byte entries = one 32-byte sector, the unit DRAM and L2 move anyway.  An entry is
+//  (fingerprint << 32 | slot index); the k-mer itself is only in the slot, which a lookup reads anyway and which
+//  confirms the match.  hcap = 4 x (distinct k-mers): a quarter of the entries are used, 1.9 % of the buckets are full,
+//  so a k-mer that is NOT in the table -- most windows of a ref read from a part of the genome the hash block does not
+//  cover, and nearly all reverse-strand windows at low coverage -- costs ONE 32-byte load and no divergent probe loop
+//  (the 16-byte-entry table with linear probing it replaces: 2.5 dependent probes per miss, 124 DRAM bytes per window,
+//  16.9 of 32 lanes active; profiles/r2l_ncu_probe_sparse.txt).  Same 32 bytes per distinct k-mer as before.
+//  A key lives in the first bucket of its probe sequence (home, home + 1, ...) that had a free entry when it was
+//  inserted; entries are never removed, so a lookup may stop at the first bucket that still has a free entry.
+__device__ __forceinline__ uint64_t ht_bucket_of(uint64_t h, uint64_t hcap) { return __umul64hi(h, hcap >> 2); }
 
-//  i-th entry of the probe sequence that starts at h0: first the eight entries of the home 128-byte line, then the
-//  next line.  `hcap` is a multiple of 8.
-__device__ __forceinline__ uint64_t ht_probe(uint64_t h0, uint32_t i, uint64_t hcap) {
-  uint64_t b = (h0 >> 3) + (i >> 3);
-  const uint64_t nb = hcap >> 3;
-  if (b >= nb) b -= nb;
-  return (b << 3) | ((h0 + i) & 7);
+template <bool NC>
+__device__ __forceinline__ void ht_load_bucket(const HashEntry *ht, uint64_t b, uint64_t (&e)[4]) {
+  if (NC) asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(ht + 4 * b));
+  else    asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(e[0]), "=l"(e[1]), "=l"(e[2]), "=l"(e[3]) : "l"(ht + 4 * b) : "memory");
 }
 
-__device__ __forceinline__ uint32_t ht_find(const HashEntry *__restrict__ ht, uint64_t hcap, uint64_t key) {
-  const uint64_t h0 = ht_home(key, hcap);
-  for (uint32_t i = 0;; i++) {
-    const uint64_t h = ht_probe(h0, i, hcap);
-    uint64_t k, v;
-    asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(k), "=l"(v) : "l"(ht + h));
-    if (k == key) return (uint32_t)v;
-    if (k == HT_EMPTY) return HT_NOTFOUND;
+//  slot index of `key`, or HT_NOTFOUND.  NC = the table and the slots are read-only for the duration of the kernel.
+template <bool NC>
+__device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, const IndexSlot *slots, uint64_t key) {
+  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
+  const uint32_t fp = (uint32_t)h;
+  for (uint64_t b = ht_bucket_of(h, hcap);;) {
+    uint64_t e[4];
+    ht_load_bucket<NC>(ht, b, e);
+    bool open = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (e[i] == HT_EMPTY) { open = true; continue; }
+      if ((uint32_t)(e[i] >> 32) != fp) continue;
+      const uint64_t *kp = &slots[(uint32_t)e[i]].key;
+      const uint64_t k = NC ? __ldg(kp) : *(const volatile uint64_t *)kp;
+      if ((k & ~OVL_SKIP_BIT) == key) return (uint32_t)e[i];
+    }
+    if (open) return HT_NOTFOUND;
+    if (++b == nb) b = 0;
   }
 }
 
 //  claims an entry for `key` (which must not be in the table yet, or be inserted by nobody else concurrently)
 __device__ __forceinline__ void ht_insert(HashEntry *ht, uint64_t hcap, uint64_t key, uint32_t idx) {
-  const uint64_t h0 = ht_home(key, hcap);
-  for (uint32_t i = 0;; i++) {
-    const uint64_t h = ht_probe(h0, i, hcap);
-    unsigned long long *kp = (unsigned long long *)&ht[h].key;
-    if (*(volatile unsigned long long *)kp != HT_EMPTY) continue;
-    if (atomicCAS(kp, (unsigned long long)HT_EMPTY, (unsigned long long)key) == HT_EMPTY) { ht[h].idx = idx; return; }
+  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
+  const unsigned long long val = ((unsigned long long)(uint32_t)h << 32) | idx;
+  for (uint64_t b = ht_bucket_of(h, hcap);;) {
+    unsigned long long *p = reinterpret_cast<unsigned long long *>(ht + 4 * b);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (*(volatile unsigned long long *)(p + i) == HT_EMPTY && atomicCAS(p + i, (unsigned long long)HT_EMPTY, val) == HT_EMPTY) return;
+    if (++b == nb) b = 0;
   }
 }
 
@@ -1030,7 +1050,7 @@ __global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip,
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_skip) return;
   const uint64_t key = skip[i];
-  const uint32_t idx = ht_find(ht, hcap, key);
+  const uint32_t idx = ht_find<false>(ht, hcap, slots, key);
   if (idx == HT_NOTFOUND) {
     const uint32_t j = n_distinct + (uint32_t)atomicAdd(n_extra, 1ull);
     uint4 *sp = reinterpret_cast<uint4 *>(&slots[j]);
@@ -1080,9 +1100,20 @@ __device__ __forceinline__ bool slot_at(const IndexSlot *__restrict__ slots, uin
 //  full lookup through the hash table; returns the path index or HT_NOTFOUND
 __device__ __forceinline__ uint32_t slot_lookup(const IndexSlot *__restrict__ slots, const HashEntry *__restrict__ ht, uint64_t hcap,
                                                 uint64_t key, SlotView &v) {
-  const uint32_t idx = ht_find(ht, hcap, key);
-  if (idx != HT_NOTFOUND) slot_at(slots, idx, key, v);
-  return idx;
+  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
+  const uint32_t fp = (uint32_t)h;
+  for (uint64_t b = ht_bucket_of(h, hcap);;) {
+    uint64_t e[4];
+    ht_load_bucket<true>(ht, b, e);
+    bool open = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (e[i] == HT_EMPTY) { open = true; continue; }
+      if ((uint32_t)(e[i] >> 32) == fp && slot_at(slots, (uint32_t)e[i], key, v)) return (uint32_t)e[i];
+    }
+    if (open) return HT_NOTFOUND;
+    if (++b == nb) b = 0;
+  }
 }
 
 #define SMALL_ITEM_MAX 8u
@@ -1122,13 +1153,14 @@ __device__ __forceinline__ void stage_append(ItemStage &S, bool has, uint4 item,
 //  lane whose k-mer is there is done.  After PROBE_ROUNDS such rounds the lanes still unresolved (windows with read
 //  errors, path breaks) look themselves up through the hash table, in parallel.
 #define PROBE_ROUNDS 3
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, const uint64_t *__restrict__ woff,
             const uint32_t *__restrict__ len, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
             uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint32_t n_slots,
             const HashEntry *__restrict__ ht, uint64_t hcap,
             uint32_t *__restrict__ ref_valid, uint32_t *rflags,
-            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work, bool one_list) {
+            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work, int flags) {
+  const bool one_list = flags & 1, adaptive = flags & 2;
   __shared__ uint4 stage[WARPS_PER_BLOCK][STAGE_SMALL + STAGE_LARGE];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -1143,6 +1175,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
     const uint64_t gg_end = min(total, (ch + 1) * PROBE_CHUNK);
     uint32_t prev_r = 0xFFFFFFFFu; int prev_dir = -1; unsigned prev_top = 0;
     uint32_t next_idx = HT_NOTFOUND;                          // path slot expected for window p0 if the path continues
+    bool miss_mode = false;
     for (uint64_t gg = ch * PROBE_CHUNK; gg < gg_end; gg++) {
       const int dir = gg >= n_groups;
       const uint64_t g = dir ? gg - n_groups : gg;
@@ -1159,14 +1192,20 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       uint32_t my_idx = HT_NOTFOUND;
       {
         unsigned need = __ballot_sync(0xffffffffu, ok);
+        const unsigned n_ok = __popc(need);
         uint32_t base = carried ? next_idx : HT_NOTFOUND;
-        for (int round = 0; need && round < PROBE_ROUNDS; round++) {
+        //  miss_mode: most windows of the previous group were not in the table (a ref read from a part of the genome
+        //  the hash block does not cover: 85 % of the windows of a human-size job).  There is no path to follow there,
+        //  and one lane looking itself up per round is a chain of dependent DRAM latencies: all lanes go straight to
+        //  the hash table, in parallel.
+        for (int round = 0; need && round < PROBE_ROUNDS && !(miss_mode && base == HT_NOTFOUND); round++) {
           const int j = __ffs(need) - 1;
           if (base == HT_NOTFOUND) {                            // lane j finds its own slot; the others follow it
             uint32_t ij = HT_NOTFOUND;
             if (lane == j) { ij = slot_lookup(slots, ht, hcap, key, v); my_idx = ij; }
             ij = __shfl_sync(0xffffffffu, ij, j);
             need &= ~(1u << j);
+            if (ij == HT_NOTFOUND && adaptive) break;           // no path here either: the rest in parallel
             if (ij == HT_NOTFOUND || !need) continue;
             base = ij - (uint32_t)j;
           }
@@ -1180,6 +1219,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
         if ((need >> lane) & 1u) my_idx = slot_lookup(slots, ht, hcap, key, v);
         const uint32_t last = __shfl_sync(0xffffffffu, my_idx, 31);
         next_idx = (last == HT_NOTFOUND) ? HT_NOTFOUND : last + 1;
+        miss_mode = adaptive && 2 * __popc(__ballot_sync(0xffffffffu, my_idx != HT_NOTFOUND)) < n_ok;
       }
       if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
         uint32_t f = 0;
@@ -1922,7 +1962,7 @@ int ovl_build_index(ovlb_ctx *c) {
   skip.erase(std::unique(skip.begin(), skip.end()), skip.end());
   const uint64_t nd = X.n_distinct, ns = nd + skip.size();
   if (ns >= 0xFFFFFFF0ull) { ovl_set_error("too many distinct k-mers for one index (>= 2^32); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
-  uint64_t hcap = ((2 * ns + 64) + 7) & ~7ull;            // whole 128-byte lines of eight entries, load <= 0.5
+  uint64_t hcap = (4 * ns + 64) & ~3ull;                   // 8-byte entries in buckets of four, a quarter of them used
   if ((rc = ensure(X.slots, X.slots_cap, (size_t)ns + 1, 9, 8))) return rc;
   if (!tmp_ready) {
     if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)nd + 1, 9, 8))) return rc;
@@ -2028,7 +2068,8 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
     if (per_sm < 1) per_sm = 1;
     k_ref_probe<<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
         R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.n_slots, X.htab, X.hcap,
-        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work, getenv("OVLB_EXPAND_OLD") == nullptr);
+        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work,
+        (getenv("OVLB_EXPAND_OLD") == nullptr ? 1 : 0) | (getenv("OVLB_PROBE_SERIAL") == nullptr ? 2 : 0));
     c->launches++;
   }
   CK(cudaGetLastError());

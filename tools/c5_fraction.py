@@ -62,6 +62,7 @@ def main():
     ap.add_argument("--procs", type=int, default=16)
     ap.add_argument("--store", default="/tmp/c5frac")
     ap.add_argument("--out", default="")
+    ap.add_argument("--ncu-launches", default="", help="third run under `ncu --metrics gpu__time_duration.sum`: the launch list goes to this CSV (not timed)")
     args = ap.parse_args()
     os.makedirs(args.store, exist_ok=True)
     t0 = time.perf_counter()
@@ -105,6 +106,9 @@ def main():
         f = {k: float(v) for k, v in re.findall(r"(create|pack-hash|load\+index|pack-ref|stage|run|fetch|submit)\s+([0-9.]+)", ph)}
         tiles = len([ln for ln in log.splitlines() if "Processed reads" in ln])
         rows.append(dict(wall_s=round(wall, 2), tiles=tiles, overlaps=int(m.group(1)), pairs=int(m.group(2)), phases=f))
+    if args.ncu_launches:
+        subprocess.run(["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "--csv", "--log-file", args.ncu_launches] + cmd,
+                       capture_output=True)
     f = rows[-1]["phases"]; tiles = rows[-1]["tiles"]
     total_bases = args.genome * args.coverage
     n_blocks = total_bases / b_hash
