@@ -527,7 +527,7 @@ def main():
             "index_sort_ms": ("k_part2 (coarse partition -> buckets, 8-byte tuples)", 1, hk * (16 + 8)),
             "index_table_ms": ("k_bucket_group2 (bulk-copy fed) + first-position bitmap + k_path_slots2", 1, hk * (8 + 4)),
             "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),
-            "expand_ms": ("k_expand_small + k_expand_large", 1, sr * (4 + 16 + 16)),
+            "expand_ms": ("k_expand_coop", 1, sr * (4 + 16 + 16)),
             "sort_ms": ("radix sort of the seed runs", 8, sr * 16 * 2),
             "chain_ms": ("k_pair_scatter + k_chain_pairs", 1, sr * (16 + 12 + 12 + 16)),
         }

@@ -1838,9 +1838,11 @@ int ovl_build_index(ovlb_ctx *c) {
     int B = 2 * K + 3 < 8 ? 2 * K + 3 : 8; while (B < 2 * K && (n >> B) > BK_TARGET) B++;
     int posbits = 1; while (posbits < 32 && (n >> posbits)) posbits++;
     if (bucketed && (2 * K + 3 - B + posbits > 64 || B > 20 || B < 2)) bucketed = false;
-    const uint64_t tmp_cap = n / 4 * 3 + (1u << 20);
-    //  the bucketed build sizes its slot scratch for the worst case (3/4 of the tuples distinct) before it knows the
-    //  real count; if that does not fit a third of the memory budget use the sorted build, which counts first
+    //  the bucketed build sizes its slot scratch before it knows the number of distinct k-mers: for every tuple distinct
+    //  (a block of a large job covers its part of the genome less than once) if that fits a third of the memory budget,
+    //  else for 3/4 of them; if that does not fit either use the sorted build, which counts first
+    uint64_t tmp_cap = n + (1u << 20);
+    if (tmp_cap * (sizeof(IndexSlot) + 8) > c->mem_budget / 3) tmp_cap = n / 4 * 3 + (1u << 20);
     if (bucketed && tmp_cap * (sizeof(IndexSlot) + 8) > c->mem_budget / 3) bucketed = false;
 
     if (bucketed) {
