@@ -343,10 +343,13 @@ int main(int argc, char **argv) {
   //  Re-block the job inside the process (the output does not depend on blocking): hash blocks
   //  sized for HBM, ref batches sized for the device seed buffers -- and small enough that every GPU gets several.
   //  Hash block from the memory a context gets: ovlb_build_index needs, per hash base, 1 B of dp4 reads (both
-  //  orientations) + 24 B of tuple scratch (key, partitioned key, position, occurrence) and, per DISTINCT k-mer, ~120 B
-  //  (slot, scratch slot, two 16 B table entries at load 0.5, path-sort pairs) -- and in a large job most k-mers of a
-  //  block are distinct (a block covers the genome a few times at most), so the model is ~150 B per base.  The ref
-  //  batch, the seed buffers and the extension scratch share the other half of the budget.
+  //  orientations) + ~40 B of tuple scratch (16 B partition records, 12 - 24 B of bucket tuples, occurrence) and, per
+  //  DISTINCT k-mer, ~100 B (slot, scratch slot + first position, 32 B of table buckets) -- and in a large job most
+  //  k-mers of a block are distinct (a block covers the genome less than once), so the model is 150 B per base.
+  //  Everything else is taken off the budget first: the seed-run buffers (1/12 of it, ovl_index.cu), the extension
+  //  scratch (from the longest read and the error rate, at most 1/4, ovl_extend.cu), two ref slots and the records.
+  //  Bigger blocks mean fewer tiles: every ref window is looked up once per hash block, and where most lookups miss
+  //  (a human-size job) a tile costs the same whatever the block holds.
   uint64_t minBudget = ~0ull;
   for (uint32_t wi = 0; wi < (uint32_t)G.gpus.size(); wi++) {
     const int d = G.gpus[wi];
@@ -354,9 +357,18 @@ int main(int argc, char **argv) {
     if (ovlb_device_total_memory(d, &tot)) FAIL("ERROR: %s", ovlb_last_error());   // device's context here, serially over the GPUs
     minBudget = std::min<uint64_t>(minBudget, (uint64_t)((double)tot * 0.95 * 0.8 / sharers[wi]));
   }
-  const uint64_t hashBlockModel = std::max<uint64_t>(minBudget / 2 / 150, 1000000ull);
+  const uint64_t refBatchDefault = 256000000ull;
+  uint64_t runSide = minBudget / 12;
+  {
+    const double em = G.maxErate * (double)maxLen + 64;                  // rows of the longest extension
+    const double perWarp = (em * em / 32 + em) * 8 + em * 64 + 4096;     // from-code arena + HBM rings + per-row arrays
+    runSide += (uint64_t)std::min<double>((double)minBudget / 4, 1.3 * perWarp * 148 * 32);
+    runSide += 2 * 3 * (G.refBatchBases ? G.refBatchBases : refBatchDefault) + (3ull << 30);   // two ref slots (dp4 both strands, groups, hit words), records, slack
+  }
+  const uint64_t blockSide = minBudget > runSide ? (uint64_t)((double)(minBudget - runSide) * 0.9) : 0;
+  const uint64_t hashBlockModel = std::max<uint64_t>(blockSide / 150, 1000000ull);
   const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : std::min<uint64_t>(1500000000ull, hashBlockModel);
-  uint64_t refBatch = G.refBatchBases ? G.refBatchBases : 256000000ull;
+  uint64_t refBatch = G.refBatchBases ? G.refBatchBases : refBatchDefault;
   //  Several workers: every one should get a few tiles of each hash block so that longest-first assignment can balance
   //  them, but not many small ones -- an extension launch cannot end before its slowest pair does (0.2 - 1 s on noisy
   //  reads, tools/scale_run.py), so a tile should hold tens of pairs per resident warp.

@@ -3,6 +3,7 @@
 
   self     : ref batch == hash block (a bacterial job, the first tile of every hash block): every window is in the table and
              the path-ordered slots are read coalesced;
+  dense    : ref batch == hash block at 50x coverage (bench.py's C2 tile): both strands of every window hit;
   sparse   : hash block and ref batch are DIFFERENT reads sampled uniformly from a genome much larger than either (the tile
              grid of a human-size job, BASELINE configs[4]): ~85 % of the windows are not in the table, the rest hit in
              stretches.
@@ -51,6 +52,7 @@ def main():
     ap.add_argument("--genome", type=float, default=400e6)
     ap.add_argument("--hash-bases", type=float, default=60e6)
     ap.add_argument("--ref-bases", type=float, default=120e6)
+    ap.add_argument("--dense-genome", type=float, default=5e6, help="also time the C2 tile (this genome x 50x, ref == hash); 0 = skip")
     args = ap.parse_args()
     G = synth.make_genome(int(args.genome), seed=5)
     ref = sample(G, args.ref_bases, 1)
@@ -60,6 +62,12 @@ def main():
     del G
     r = time_probe(hsh, hsh, 1, 1)
     print(json.dumps(dict(regime="self", hash_reads=len(hsh), **r)), flush=True)
+    del hsh, ref
+    if args.dense_genome > 0:                                              # the C2 tile of bench.py: every window hits, both strands
+        G = synth.make_genome(int(args.dense_genome), seed=2001)
+        d = synth.simulate_reads(G, 50.0, 3000, 30000, 0.001, seed=2002, lognormal=(9.25, 0.3))
+        r = time_probe(d, d, 1, 1)
+        print(json.dumps(dict(regime="dense", hash_reads=len(d), **r)), flush=True)
 
 
 if __name__ == "__main__":
