@@ -118,6 +118,7 @@ struct ovlb_ctx {
   DevCounters *d_counters = nullptr;
   ExtScratch   ext;
   uint64_t     mem_budget = 0;
+  uint32_t     ht_fpmask = 0xFFFFFFFFu;   // source of the async copy to the device symbol (must outlive the call)
   int          sm_count = 148;
   int          bucket_tb = 11;            // table bits k_bucket_group2 starts with (12 once a block needed the large table)
   bool         bucket_attr_set = false;   // k_bucket_group's dynamic shared-memory size was raised on this context's device

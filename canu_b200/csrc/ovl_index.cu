@@ -383,6 +383,11 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
 //  A key lives in the first bucket of its probe sequence (home, home + 1, ...) that had a free entry when it was
 //  inserted; entries are never removed, so a lookup may stop at the first bucket that still has a free entry.
 __device__ __forceinline__ uint64_t ht_bucket_of(uint64_t h, uint64_t hcap) { return __umul64hi(h, hcap >> 2); }
+//  fingerprint = low bits of the multiplicative hash (the bucket comes from its high bits).  The mask is all ones except
+//  in tests, which narrow it (OVLB_HT_FPMASK) so that different k-mers of a bucket share fingerprints and the
+//  confirm-by-slot-and-go-on path is exercised.
+__device__ uint32_t g_ht_fpmask = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t ht_fp_of(uint64_t h) { return (uint32_t)h & g_ht_fpmask; }
 
 template <bool NC>
 __device__ __forceinline__ void ht_load_bucket(const HashEntry *ht, uint64_t b, uint64_t (&e)[4]) {
@@ -394,7 +399,7 @@ __device__ __forceinline__ void ht_load_bucket(const HashEntry *ht, uint64_t b, 
 template <bool NC>
 __device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, const IndexSlot *slots, uint64_t key) {
   const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const uint32_t fp = (uint32_t)h;
+  const uint32_t fp = ht_fp_of(h);
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     uint64_t e[4];
     ht_load_bucket<NC>(ht, b, e);
@@ -415,7 +420,7 @@ __device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, 
 //  claims an entry for `key` (which must not be in the table yet, or be inserted by nobody else concurrently)
 __device__ __forceinline__ void ht_insert(HashEntry *ht, uint64_t hcap, uint64_t key, uint32_t idx) {
   const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const unsigned long long val = ((unsigned long long)(uint32_t)h << 32) | idx;
+  const unsigned long long val = ((unsigned long long)ht_fp_of(h) << 32) | idx;
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     unsigned long long *p = reinterpret_cast<unsigned long long *>(ht + 4 * b);
 #pragma unroll
@@ -1101,7 +1106,7 @@ __device__ __forceinline__ bool slot_at(const IndexSlot *__restrict__ slots, uin
 __device__ __forceinline__ uint32_t slot_lookup(const IndexSlot *__restrict__ slots, const HashEntry *__restrict__ ht, uint64_t hcap,
                                                 uint64_t key, SlotView &v) {
   const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const uint32_t fp = (uint32_t)h;
+  const uint32_t fp = ht_fp_of(h);
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     uint64_t e[4];
     ht_load_bucket<true>(ht, b, e);
@@ -1822,10 +1827,15 @@ int ovl_build_index(ovlb_ctx *c) {
   const uint64_t sentinel = 1ull << (2 * K + 3);
 
   if ((rc = ensure_groups(c, H))) return rc;
+  {
+    const char *ev = getenv("OVLB_HT_FPMASK");                          // read per build: a test narrows it for one case
+    c->ht_fpmask = ev ? (uint32_t)strtoul(ev, nullptr, 0) : 0xFFFFFFFFu;
+    CK(cudaMemcpyToSymbolAsync(g_ht_fpmask, &c->ht_fpmask, 4, 0, cudaMemcpyHostToDevice, c->stream));
+  }
 
   //  Bucketed build (default) or sorted build (OVLB_BUCKETED=0, or after a bucket overflowed)
-  static const int bucketed_env = [] { const char *ev = getenv("OVLB_BUCKETED"); return ev ? atoi(ev) : 1; }();   // thread-safe init
-  bool bucketed = bucketed_env != 0;
+  bool bucketed = true;
+  if (const char *ev = getenv("OVLB_BUCKETED")) bucketed = atoi(ev) != 0;   // read per build: the tests run both builds in one process
   const uint64_t mixc = 0x9E3779B97F4A7C15ull;
   uint64_t mix_inv = mixc;                                              // inverse mod 2^64 by Newton iteration
   for (int i = 0; i < 6; i++) mix_inv *= 2 - mixc * mix_inv;

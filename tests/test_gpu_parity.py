@@ -403,6 +403,45 @@ def test_other_kmer_lengths_through_the_bucketed_build(K, expect_bucketed):
     assert ctr["kmer_hits_with_olap"] == st["kmer_hits_with_olap"] and ctr["kmer_hits_without_olap"] == st["kmer_hits_without_olap"]
 
 
+@pytest.mark.parametrize("sorted_build", [False, True])
+def test_hash_table_fingerprint_collisions_are_resolved_by_the_slot(monkeypatch, sorted_build):
+    """The index hash table keeps a 32-bit fingerprint per entry, not the k-mer; the slot confirms a match.  With the
+    fingerprint narrowed to 2 bits (test hook OVLB_HT_FPMASK) nearly every bucket holds different k-mers with the same
+    fingerprint, so lookups must go on past false candidates -- records, counters and the skip-k-mer marking (which
+    looks k-mers up and inserts absent ones) must not change.  A ref batch of other reads exercises the miss path."""
+    from canu_b200 import synth
+    api = _api()
+    g = synth.make_genome(80000, seed=301, repeat_len=300, repeat_copies=12)
+    hreads = synth.simulate_reads(g, 10, 1500, 4000, 0.01, seed=302)
+    rreads = synth.simulate_reads(g, 6, 1500, 4000, 0.01, seed=303)
+    rng = np.random.default_rng(304)
+    skip = [bytes(b"ACGT"[j] for j in rng.integers(0, 4, 22)) for _ in range(500)]             # absent k-mers (appended to the index)
+    skip += [hreads[3][i:i + 22].tobytes() for i in range(0, 1500, 7)]                         # and present ones (flagged)
+    skip = sorted(set(k for k in skip if b"N" not in k))
+
+    def run():
+        if sorted_build:
+            monkeypatch.setenv("OVLB_BUCKETED", "0")
+        prm = api.OverlapParams(kmer_len=22, max_erate=0.045, min_olap_len=500, max_read_len=max(r.size for r in hreads + rreads))
+        ov = api.Overlapper(prm)
+        ph = api.PackedReads(hreads, first_read_id=len(rreads) + 1, min_len=500)
+        pr = api.PackedReads(rreads, first_read_id=1, min_len=500)
+        ov.load_hash_reads(ph); ov.mark_skip_kmers(skip); ov.build_index()
+        a = np.sort(ov.overlap_ref_batch(pr, cap=1 << 20), order=["a_iid", "b_iid", "w0", "w1"])
+        c = ov.counters()
+        ov.close()
+        return a, c
+
+    want, cw = run()
+    monkeypatch.setenv("OVLB_HT_FPMASK", "0x3")
+    got, cg = run()
+    assert len(want) > 100 and len(got) == len(want)
+    for f in ("a_iid", "b_iid", "w0", "w1"):
+        assert np.array_equal(got[f], want[f]), f
+    drop = ("ext_busy_ns", "ext_capacity_ns")
+    assert {k: v for k, v in cg.items() if k not in drop} == {k: v for k, v in cw.items() if k not in drop}
+
+
 @pytest.mark.parametrize("homopoly", [False, True])
 def test_reads_prepared_on_the_device_match_reads_prepared_on_the_host(homopoly):
     """Row f3: sqStore blobs uploaded as stored, homopolymer compression (sequence-v1.C:203-261) and clear-range trimming
