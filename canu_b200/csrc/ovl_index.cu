@@ -369,6 +369,12 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
 //  gives, whatever the load width).  `htab` (below) is only consulted where the path breaks: a read start, an error, the
 //  border between two first-coverage stretches -- and for every window whose k-mer is not in the block at all.
 //  ------------------------------------------------------------------------------------------------
+//  reverse complement of a k-mer key (base j in bits 2j..2j+1, A0 C1 G2 T3): complement = ~code, order reversed
+__device__ __forceinline__ uint64_t kmer_rc(uint64_t key, int K) {
+  uint64_t x = __brevll(~key) >> (64 - 2 * K);                            // pairs reversed, bits inside a pair swapped
+  return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
 #define HT_EMPTY   0xFFFFFFFFFFFFFFFFull
 #define HT_NOTFOUND 0xFFFFFFFFu
 #define HT_MULT    0x9E3779B97F4A7C15ull
@@ -382,12 +388,20 @@ __device__ __forceinline__ uint32_t gallop_lower_bound(const uint64_t *__restric
 //  16.9 of 32 lanes active; profiles/r2l_ncu_probe_sparse.txt).  Same 32 bytes per distinct k-mer as before.
 //  A key lives in the first bucket of its probe sequence (home, home + 1, ...) that had a free entry when it was
 //  inserted; entries are never removed, so a lookup may stop at the first bucket that still has a free entry.
+//  The bucket and the fingerprint come from the CANONICAL k-mer (the smaller of the k-mer and its reverse complement):
+//  a k-mer and its reverse complement are different keys with different slots, but they share a probe sequence, so the
+//  one bucket load that looks a forward window up also says whether the reverse-strand window over the same bases can
+//  be in the table (slot_lookup_fr below) -- half the random loads of a job whose windows mostly miss.
+__device__ __forceinline__ uint64_t ht_hash_of(uint64_t key, uint64_t rkey) { return (key < rkey ? key : rkey) * HT_MULT; }
 __device__ __forceinline__ uint64_t ht_bucket_of(uint64_t h, uint64_t hcap) { return __umul64hi(h, hcap >> 2); }
 //  fingerprint = low bits of the multiplicative hash (the bucket comes from its high bits).  The mask is all ones except
 //  in tests, which narrow it (OVLB_HT_FPMASK) so that different k-mers of a bucket share fingerprints and the
 //  confirm-by-slot-and-go-on path is exercised.
 __device__ uint32_t g_ht_fpmask = 0xFFFFFFFFu;
 __device__ __forceinline__ uint32_t ht_fp_of(uint64_t h) { return (uint32_t)h & g_ht_fpmask; }
+//  ... and the lowest fingerprint bit says which of the two this entry is (0 = the canonical form), so that a lookup
+//  does not have to read the slot of the other strand's entry to tell them apart
+__device__ __forceinline__ uint32_t ht_fp2(uint64_t h, uint64_t key, uint64_t rkey) { return (ht_fp_of(h) & ~1u) | (key > rkey ? 1u : 0u); }
 
 template <bool NC>
 __device__ __forceinline__ void ht_load_bucket(const HashEntry *ht, uint64_t b, uint64_t (&e)[4]) {
@@ -397,9 +411,10 @@ __device__ __forceinline__ void ht_load_bucket(const HashEntry *ht, uint64_t b, 
 
 //  slot index of `key`, or HT_NOTFOUND.  NC = the table and the slots are read-only for the duration of the kernel.
 template <bool NC>
-__device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, const IndexSlot *slots, uint64_t key) {
-  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const uint32_t fp = ht_fp_of(h);
+__device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, const IndexSlot *slots, uint64_t key, int K) {
+  const uint64_t rkey = kmer_rc(key, K);
+  const uint64_t h = ht_hash_of(key, rkey), nb = hcap >> 2;
+  const uint32_t fp = ht_fp2(h, key, rkey);
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     uint64_t e[4];
     ht_load_bucket<NC>(ht, b, e);
@@ -418,9 +433,10 @@ __device__ __forceinline__ uint32_t ht_find(const HashEntry *ht, uint64_t hcap, 
 }
 
 //  claims an entry for `key` (which must not be in the table yet, or be inserted by nobody else concurrently)
-__device__ __forceinline__ void ht_insert(HashEntry *ht, uint64_t hcap, uint64_t key, uint32_t idx) {
-  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const unsigned long long val = ((unsigned long long)ht_fp_of(h) << 32) | idx;
+__device__ __forceinline__ void ht_insert(HashEntry *ht, uint64_t hcap, uint64_t key, uint32_t idx, int K) {
+  const uint64_t rkey = kmer_rc(key, K);
+  const uint64_t h = ht_hash_of(key, rkey), nb = hcap >> 2;
+  const unsigned long long val = ((unsigned long long)ht_fp2(h, key, rkey) << 32) | idx;
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     unsigned long long *p = reinterpret_cast<unsigned long long *>(ht + 4 * b);
 #pragma unroll
@@ -481,14 +497,14 @@ k_group_heads(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ oc
 //  one thread per path position: gather the slot into place and publish it in the hash table
 __global__ void __launch_bounds__(256)
 k_path_slots(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ order, uint32_t n, IndexSlot *__restrict__ slots,
-             HashEntry *ht, uint64_t hcap) {
+             HashEntry *ht, uint64_t hcap, int K) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint4 *src = reinterpret_cast<const uint4 *>(&tmp[order[j]]);
   const uint4 a = src[0], b = src[1];
   uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
   dst[0] = a; dst[1] = b;
-  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j);
+  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j, K);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -552,12 +568,6 @@ __device__ __forceinline__ void spill_add(const Spill &S, uint64_t km) {
     h = (h + 1) & S.mask;
   }
   atomicOr(S.flag, 4ull);                                                 // table full
-}
-
-//  reverse complement of a k-mer key (base j in bits 2j..2j+1, A0 C1 G2 T3): complement = ~code, order reversed
-__device__ __forceinline__ uint64_t kmer_rc(uint64_t key, int K) {
-  uint64_t x = __brevll(~key) >> (64 - 2 * K);                            // pairs reversed, bits inside a pair swapped
-  return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
 }
 
 //  CENSUS = k-mer counting for the skip list (ovl_kmer_census): the tuple key is the CANONICAL k-mer (smaller of the
@@ -926,7 +936,7 @@ k_bm_prefix(const uint32_t *__restrict__ bm, uint64_t n_words, const uint32_t *_
 __global__ void __launch_bounds__(256)
 k_path_slots2(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ first_pos, uint32_t n,
               const uint32_t *__restrict__ bm, const uint32_t *__restrict__ wprefix,
-              IndexSlot *__restrict__ slots, HashEntry *ht, uint64_t hcap) {
+              IndexSlot *__restrict__ slots, HashEntry *ht, uint64_t hcap, int K) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   const uint32_t fp = first_pos[c];
@@ -935,7 +945,7 @@ k_path_slots2(const IndexSlot *__restrict__ tmp, const uint32_t *__restrict__ fi
   const uint4 a = src[0], b = src[1];
   uint4 *dst = reinterpret_cast<uint4 *>(&slots[j]);
   dst[0] = a; dst[1] = b;
-  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j);
+  ht_insert(ht, hcap, (uint64_t)a.x | ((uint64_t)a.y << 32), j, K);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1055,14 +1065,14 @@ __global__ void k_index_skip(const uint64_t *__restrict__ skip, uint64_t n_skip,
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_skip) return;
   const uint64_t key = skip[i];
-  const uint32_t idx = ht_find<false>(ht, hcap, slots, key);
+  const uint32_t idx = ht_find<false>(ht, hcap, slots, key, K);
   if (idx == HT_NOTFOUND) {
     const uint32_t j = n_distinct + (uint32_t)atomicAdd(n_extra, 1ull);
     uint4 *sp = reinterpret_cast<uint4 *>(&slots[j]);
     const uint64_t kk = key | OVL_SKIP_BIT;
     sp[0] = make_uint4((uint32_t)kk, (uint32_t)(kk >> 32), 0, 0);
     sp[1] = make_uint4(0, 0, 0, 0);
-    ht_insert(ht, hcap, key, j);
+    ht_insert(ht, hcap, key, j, K);
     return;
   }
   atomicOr((unsigned long long *)&slots[idx].key, (unsigned long long)OVL_SKIP_BIT);
@@ -1102,23 +1112,45 @@ __device__ __forceinline__ bool slot_at(const IndexSlot *__restrict__ slots, uin
   return true;
 }
 
-//  full lookup through the hash table; returns the path index or HT_NOTFOUND
+//  Full lookup through the hash table; returns the path index or HT_NOTFOUND.  FR (the lookup of a FORWARD window)
+//  also learns whether the reverse complement of the k-mer -- the k-mer of the reverse-strand window over the same
+//  bases -- can be in the table: `rc_absent` is set only if it certainly is not (no entry of the probe sequence
+//  carries the other strand's fingerprint).  The four entries of a bucket are compared first and the candidates (one,
+//  as good as always) confirmed by their slot in a loop, so that the 32-byte slot load is in the code once.
+template <bool FR>
 __device__ __forceinline__ uint32_t slot_lookup(const IndexSlot *__restrict__ slots, const HashEntry *__restrict__ ht, uint64_t hcap,
-                                                uint64_t key, SlotView &v) {
-  const uint64_t h = key * HT_MULT, nb = hcap >> 2;
-  const uint32_t fp = ht_fp_of(h);
+                                                uint64_t key, int K, SlotView &v, bool &rc_absent) {
+  //  keep the hash arithmetic (~45 instructions) inside the branch that looks up: it is loop-invariant, and the compiler
+  //  otherwise hoists it in front of the probe kernel's round loop, where every lane of every group pays for it
+  //  although most groups of a well-covered block never touch the table (ncu: 11 % of the kernel's instructions)
+  asm volatile("" : "+l"(key));
+  const uint64_t rkey = kmer_rc(key, K);
+  const uint64_t h = ht_hash_of(key, rkey), nb = hcap >> 2;
+  const uint32_t fp = ht_fp2(h, key, rkey);
+  uint32_t found = HT_NOTFOUND;
+  bool r_seen = rkey == key;                                             // a palindrome is its own reverse complement
   for (uint64_t b = ht_bucket_of(h, hcap);;) {
     uint64_t e[4];
     ht_load_bucket<true>(ht, b, e);
     bool open = false;
+    unsigned cand = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (e[i] == HT_EMPTY) { open = true; continue; }
-      if ((uint32_t)(e[i] >> 32) == fp && slot_at(slots, (uint32_t)e[i], key, v)) return (uint32_t)e[i];
+      const uint32_t f = (uint32_t)(e[i] >> 32);
+      open |= e[i] == HT_EMPTY;
+      if (f == fp && e[i] != HT_EMPTY) cand |= 1u << i;
+      if (FR && f == (fp ^ 1u)) r_seen = true;                            // may be the other strand's entry: no need to know for sure
     }
-    if (open) return HT_NOTFOUND;
+    while (cand && found == HT_NOTFOUND) {
+      const int i = __ffs(cand) - 1; cand &= cand - 1;
+      const uint32_t idx = (uint32_t)(i == 0 ? e[0] : i == 1 ? e[1] : i == 2 ? e[2] : e[3]);
+      if (slot_at(slots, idx, key, v)) found = idx;
+    }
+    if (open || (found != HT_NOTFOUND && (!FR || r_seen))) break;
     if (++b == nb) b = 0;
   }
+  rc_absent = FR && !r_seen;
+  return found;
 }
 
 #define SMALL_ITEM_MAX 8u
@@ -1158,13 +1190,15 @@ __device__ __forceinline__ void stage_append(ItemStage &S, bool has, uint4 item,
 //  lane whose k-mer is there is done.  After PROBE_ROUNDS such rounds the lanes still unresolved (windows with read
 //  errors, path breaks) look themselves up through the hash table, in parallel.
 #define PROBE_ROUNDS 3
+template <int DIR>
 __global__ void __launch_bounds__(THREADS, 4)
 k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, const uint64_t *__restrict__ woff,
             const uint32_t *__restrict__ len, const uint64_t *__restrict__ pbase, const uint32_t *__restrict__ grp_read,
             uint64_t n_groups, uint64_t n_pos, int K, const IndexSlot *__restrict__ slots, uint32_t n_slots,
             const HashEntry *__restrict__ ht, uint64_t hcap,
             uint32_t *__restrict__ ref_valid, uint32_t *rflags,
-            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work, int flags) {
+            uint4 *__restrict__ item_small, uint4 *__restrict__ item_large, uint64_t item_cap, unsigned long long *work, int flags,
+            uint32_t *rc_absent, uint64_t gg_lo, uint64_t gg_hi) {
   const bool one_list = flags & 1, adaptive = flags & 2;
   __shared__ uint4 stage[WARPS_PER_BLOCK][STAGE_SMALL + STAGE_LARGE];
   const int lane = threadIdx.x & 31;
@@ -1173,17 +1207,21 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
   SS.buf = stage[wib];               SS.n = 0; SS.cap = one_list ? STAGE_SMALL + STAGE_LARGE : STAGE_SMALL; SS.out = item_small; SS.counter = &work[3]; SS.out_cap = item_cap;
   SL.buf = stage[wib] + STAGE_SMALL; SL.n = 0; SL.cap = STAGE_LARGE; SL.out = item_large; SL.counter = &work[4]; SL.out_cap = item_cap;
 
-  const uint64_t total = 2 * n_groups;
-  const uint64_t n_chunks = (total + PROBE_CHUNK - 1) / PROBE_CHUNK;
+  //  One launch per orientation, [gg_lo, gg_hi) = [0, n_groups) then [n_groups, 2 n_groups): the forward pass leaves
+  //  in `rc_absent` (one bit per position of the ref batch, reverse-strand coordinates) the windows whose k-mer it has
+  //  SEEN to be missing from the table while looking up the forward window over the same bases; the reverse pass does
+  //  not look those up.
+  const uint64_t n_chunks = (gg_hi - gg_lo + PROBE_CHUNK - 1) / PROBE_CHUNK;
   KmerWindow KW; KW.w = nullptr; KW.w0 = 0; KW.codes = 0; KW.inv = 0xFFFFu;
   for (uint64_t ch = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + wib; ch < n_chunks; ch += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
-    const uint64_t gg_end = min(total, (ch + 1) * PROBE_CHUNK);
+    const uint64_t gg_end = min(gg_hi, gg_lo + (ch + 1) * PROBE_CHUNK);
     uint32_t prev_r = 0xFFFFFFFFu; int prev_dir = -1; unsigned prev_top = 0;
     uint32_t next_idx = HT_NOTFOUND;                          // path slot expected for window p0 if the path continues
     bool miss_mode = false;
-    for (uint64_t gg = ch * PROBE_CHUNK; gg < gg_end; gg++) {
-      const int dir = gg >= n_groups;
+    for (uint64_t gg = gg_lo + ch * PROBE_CHUNK; gg < gg_end; gg++) {
+      constexpr int dir = DIR;
       const uint64_t g = dir ? gg - n_groups : gg;
+      const uint32_t absent_w = dir ? __ldcg(rc_absent + g) : 0u;   // issued first: nothing below depends on it until the lookups
       const uint32_t r = grp_read[g];
       const int L = (int)len[r];
       const int p0 = (int)(g * 32 - pbase[r]);
@@ -1192,7 +1230,9 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
       const bool carried = (r == prev_r && dir == prev_dir);    // the previous iteration was window group p0-32 of this read
 
       uint64_t key; int cls;
-      const bool ok = warp_kmers_win(KW, w, p0, L, K, lane, key, cls);
+      bool ok = warp_kmers_win(KW, w, p0, L, K, lane, key, cls);
+      if (dir) ok = ok && !((absent_w >> lane) & 1u);
+      bool r_absent = false;                                  // forward pass: my k-mer's reverse complement is not in the table
       SlotView v; v.found = false; v.skip = false; v.start = v.e0 = v.e1 = v.e2 = v.e3 = v.e4 = 0;
       uint32_t my_idx = HT_NOTFOUND;
       {
@@ -1206,9 +1246,8 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
         for (int round = 0; need && round < PROBE_ROUNDS && !(miss_mode && base == HT_NOTFOUND); round++) {
           const int j = __ffs(need) - 1;
           if (base == HT_NOTFOUND) {                            // lane j finds its own slot; the others follow it
-            uint32_t ij = HT_NOTFOUND;
-            if (lane == j) { ij = slot_lookup(slots, ht, hcap, key, v); my_idx = ij; }
-            ij = __shfl_sync(0xffffffffu, ij, j);
+            if (lane == j) my_idx = slot_lookup<DIR == 0>(slots, ht, hcap, key, K, v, r_absent);
+            const uint32_t ij = __shfl_sync(0xffffffffu, my_idx, j);
             need &= ~(1u << j);
             if (ij == HT_NOTFOUND && adaptive) break;           // no path here either: the rest in parallel
             if (ij == HT_NOTFOUND || !need) continue;
@@ -1221,10 +1260,24 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
           need &= ~__ballot_sync(0xffffffffu, hit);
           base = HT_NOTFOUND;
         }
-        if ((need >> lane) & 1u) my_idx = slot_lookup(slots, ht, hcap, key, v);
+        if ((need >> lane) & 1u) my_idx = slot_lookup<DIR == 0>(slots, ht, hcap, key, K, v, r_absent);
         const uint32_t last = __shfl_sync(0xffffffffu, my_idx, 31);
         next_idx = (last == HT_NOTFOUND) ? HT_NOTFOUND : last + 1;
         miss_mode = adaptive && 2 * __popc(__ballot_sync(0xffffffffu, my_idx != HT_NOTFOUND)) < n_ok;
+      }
+      if (!dir) {
+        //  forward window p covers the bases of reverse-strand window L - K - p: lane i <-> position q - i, q = L - K - p0
+        const unsigned am = __ballot_sync(0xffffffffu, r_absent);
+        if (am && lane == 0) {
+          const int q = L - K - p0;
+          unsigned rev = __brev(am);                          // bit k <-> position q - 31 + k
+          uint64_t base = pbase[r];
+          if (q >= 31) base += (uint64_t)(q - 31); else rev >>= (31 - q);    // positions below 0 belong to lanes past the last window
+          const uint64_t wd = base >> 5; const int sft = (int)(base & 31);
+          const unsigned lo = rev << sft, hi = sft ? rev >> (32 - sft) : 0u;
+          if (lo) atomicOr(&rc_absent[wd], lo);
+          if (hi) atomicOr(&rc_absent[wd + 1], hi);
+        }
       }
       if (v.found && v.skip) {                               // hi_hits (Find_Overlaps.C:274-276,310-316)
         uint32_t f = 0;
@@ -1250,7 +1303,7 @@ k_ref_probe(const uint64_t *__restrict__ fwd, const uint64_t *__restrict__ rc, c
         //  its last K-1 bases are mine and cls != 0 says base p0-1 is ACGT)
         const uint64_t pk = ((key << 2) | (uint64_t)(cls - 1)) & ((1ull << (2 * K)) - 1);
         SlotView pv; pv.found = false; pv.skip = false; pv.start = pv.e4 = 0;
-        slot_lookup(slots, ht, hcap, pk, pv);
+        bool dummy; slot_lookup<false>(slots, ht, hcap, pk, K, pv, dummy);
         prev_valid = pv.found && !pv.skip && pv.e4 > pv.start;
       }
 
@@ -1997,7 +2050,7 @@ int ovl_build_index(ovlb_ctx *c) {
     k_bm_blocksum<<<(unsigned)n_bmblk, 256, 0, c->stream>>>(bitmap, n_words, bsum);
     k_bucket_scan<<<1, 1024, 0, c->stream>>>(bsum, (uint32_t)n_bmblk, 0xFFFFFFFFu, boff);
     k_bm_prefix<<<(unsigned)n_bmblk, 256, 0, c->stream>>>(bitmap, n_words, boff, wprefix);
-    k_path_slots2<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gk, (uint32_t)nd, bitmap, wprefix, X.slots, X.htab, hcap);
+    k_path_slots2<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gk, (uint32_t)nd, bitmap, wprefix, X.slots, X.htab, hcap, K);
     c->launches += 4;
   } else if (X.n_occ) {
     if (!tmp_ready) {
@@ -2011,7 +2064,7 @@ int ovl_build_index(ovlb_ctx *c) {
     size_t tb2 = c->cub_temp_cap;
     CK(cub::DeviceRadixSort::SortPairs(c->cub_temp, tb2, X.gk, X.gk2, X.gv, X.gv2, (int64_t)nd, 0, end_bit, c->stream));
     c->launches += 2 + (end_bit + 7) / 8;
-    k_path_slots<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gv2, (uint32_t)nd, X.slots, X.htab, hcap);
+    k_path_slots<<<div_up(nd, 256), 256, 0, c->stream>>>(X.tmp_slots, X.gv2, (uint32_t)nd, X.slots, X.htab, hcap, K);
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -2050,7 +2103,9 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
   if (R.n >= (1u << OVL_RUNKEY_REF_BITS)) { ovl_set_error("ref batch has too many reads (max 262143); split it"); return OVLB_ERR_CAPACITY; }
   if (H.n >= (1u << OVL_RUNKEY_HASH_BITS)) { ovl_set_error("hash block has too many reads (max 16777215); split it"); return OVLB_ERR_CAPACITY; }
 
-  if ((rc = ensure(c->ref_valid, c->ref_valid_cap, (size_t)2 * n_groups + 80))) return rc;
+  //  hit words of both orientations | 80 words of slack | rc_absent bits (k_ref_probe)
+  if ((rc = ensure(c->ref_valid, c->ref_valid_cap, (size_t)3 * n_groups + 96))) return rc;
+  uint32_t *rc_absent = c->ref_valid + 2 * n_groups + 80;
   if ((rc = ensure_groups(c, R))) return rc;
 
   //  run and item buffers: sized from the memory budget once; overflow -> OVLB_ERR_CAPACITY
@@ -2071,18 +2126,22 @@ int ovl_seed_ref_batch(ovlb_ctx *c) {
 
   CK(cudaMemsetAsync(c->d_work, 0, 40, c->stream));       // [0] n_runs, [1] extend work cursor, [2] n_records, [3] small items, [4] large items
   CK(cudaMemsetAsync(R.flags, 0, (size_t)(R.n + 1) * 8, c->stream));
-  CK(cudaMemsetAsync(c->ref_valid + 2 * n_groups, 0, 72 * 4, c->stream));  // the run-length scan peeks up to 32 words past the word it needs
+  CK(cudaMemsetAsync(c->ref_valid + 2 * n_groups, 0, (size_t)(n_groups + 96) * 4, c->stream));  // the run-length scan peeks up to 32 words past the word it needs; rc_absent starts empty
 
   EvTimer t1(c->stream);
   if (n_groups) {
     int per_sm = 4;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ref_probe, THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ref_probe<0>, THREADS, 0);
     if (per_sm < 1) per_sm = 1;
-    k_ref_probe<<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
+    const int pflags = (getenv("OVLB_EXPAND_OLD") == nullptr ? 1 : 0) | (getenv("OVLB_PROBE_SERIAL") == nullptr ? 2 : 0);
+    //  forward windows first: they tell the reverse pass what it need not look up
+    k_ref_probe<0><<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
         R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.n_slots, X.htab, X.hcap,
-        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work,
-        (getenv("OVLB_EXPAND_OLD") == nullptr ? 1 : 0) | (getenv("OVLB_PROBE_SERIAL") == nullptr ? 2 : 0));
-    c->launches++;
+        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work, pflags, rc_absent, 0, n_groups);
+    k_ref_probe<1><<<c->sm_count * per_sm, THREADS, 0, c->stream>>>(
+        R.fwd, R.rc, R.woff, R.len, R.pbase, R.grp_read, n_groups, R.n_pos, K, X.slots, X.n_slots, X.htab, X.hcap,
+        c->ref_valid, R.flags, c->item_small, c->item_large, c->run_cap, c->d_work, pflags, rc_absent, n_groups, 2 * n_groups);
+    c->launches += 2;
   }
   CK(cudaGetLastError());
   c->timings.probe_ms = t1.stop();

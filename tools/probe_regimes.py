@@ -49,20 +49,21 @@ def time_probe(hash_reads, ref_reads, first_ref_id, first_hash_id, reps=4):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--genome", type=float, default=400e6)
+    ap.add_argument("--genome", type=float, default=400e6, help="0 = skip the sparse and self regimes")
     ap.add_argument("--hash-bases", type=float, default=60e6)
     ap.add_argument("--ref-bases", type=float, default=120e6)
     ap.add_argument("--dense-genome", type=float, default=5e6, help="also time the C2 tile (this genome x 50x, ref == hash); 0 = skip")
     args = ap.parse_args()
-    G = synth.make_genome(int(args.genome), seed=5)
-    ref = sample(G, args.ref_bases, 1)
-    hsh = sample(G, args.hash_bases, 2)
-    r = time_probe(hsh, ref, 1, len(ref) + 1)
-    print(json.dumps(dict(regime="sparse", hash_reads=len(hsh), ref_reads=len(ref), **r)), flush=True)
-    del G
-    r = time_probe(hsh, hsh, 1, 1)
-    print(json.dumps(dict(regime="self", hash_reads=len(hsh), **r)), flush=True)
-    del hsh, ref
+    if args.genome > 0:
+        G = synth.make_genome(int(args.genome), seed=5)
+        ref = sample(G, args.ref_bases, 1)
+        hsh = sample(G, args.hash_bases, 2)
+        r = time_probe(hsh, ref, 1, len(ref) + 1)
+        print(json.dumps(dict(regime="sparse", hash_reads=len(hsh), ref_reads=len(ref), **r)), flush=True)
+        del G
+        r = time_probe(hsh, hsh, 1, 1)
+        print(json.dumps(dict(regime="self", hash_reads=len(hsh), **r)), flush=True)
+        del hsh, ref
     if args.dense_genome > 0:                                              # the C2 tile of bench.py: every window hits, both strands
         G = synth.make_genome(int(args.dense_genome), seed=2001)
         d = synth.simulate_reads(G, 50.0, 3000, 30000, 0.001, seed=2002, lognormal=(9.25, 0.3))
