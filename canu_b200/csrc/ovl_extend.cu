@@ -66,8 +66,9 @@ static_assert(sizeof(DevParams) <= EXT_SM_CTL, "DevParams must fit its shared-me
 extern __shared__ __align__(16) unsigned char ext_sm[];
 
 __device__ __forceinline__ const DevParams &sh_params() { return *reinterpret_cast<const DevParams *>(ext_sm + EXT_SM_PARAMS); }
-__device__ __forceinline__ WarpCtl &sh_ctl() { return reinterpret_cast<WarpCtl *>(ext_sm + EXT_SM_CTL)[threadIdx.x >> 5]; }
-__device__ __forceinline__ int *sh_ring(int which) { return reinterpret_cast<int *>(ext_sm + EXT_SM_RINGS) + ((threadIdx.x >> 5) * 2 + which) * SRING_STRIDE; }
+__device__ __forceinline__ WarpCtl &sh_ctl(int wib) { return reinterpret_cast<WarpCtl *>(ext_sm + EXT_SM_CTL)[wib]; }
+__device__ __forceinline__ WarpCtl &sh_ctl() { return sh_ctl(threadIdx.x >> 5); }
+__device__ __forceinline__ int *sh_ring(int which, int wib) { return reinterpret_cast<int *>(ext_sm + EXT_SM_RINGS) + (wib * 2 + which) * SRING_STRIDE; }
 
 //  Number of leading positions (< lim) where A[a..] and T[t..] match; all 32 lanes cooperate, 512 bases per round.
 __device__ __forceinline__ int warp_slide(const uint64_t *A, int a, const uint64_t *T, int t, int lim, int lane) {
@@ -309,10 +310,10 @@ __device__ __forceinline__ bool cell_back(const CellState &c, int *cur, int d, i
 //  behind the base fetches at 30 warps per SM).
 template <bool SH, int U>
 __device__ __forceinline__ void dp_row_cells(int psel, int pidx, const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
-                                             int Lu, int Ru, uint32_t ngroups, int lim_e, uint2 *arena_row, int lane, RowOut &ro) {
+                                             int Lu, int Ru, uint32_t ngroups, int lim_e, uint2 *arena_row, int lane, int wib, RowOut &ro) {
   const int *prev; int *cur;
-  if (SH) { int *ring = sh_ring(0); prev = ring + psel * SRING_STRIDE; cur = ring + (psel ^ 1) * SRING_STRIDE; }
-  else    { WarpCtl &C = sh_ctl(); prev = psel ? C.gring1 : C.gring0; cur = psel ? C.gring0 : C.gring1; }
+  if (SH) { int *ring = sh_ring(0, wib); prev = ring + psel * SRING_STRIDE; cur = ring + (psel ^ 1) * SRING_STRIDE; }
+  else    { WarpCtl &C = sh_ctl(wib); prev = psel ? C.gring1 : C.gring0; cur = psel ? C.gring0 : C.gring1; }
   const uint32_t *A32 = reinterpret_cast<const uint32_t *>(A), *T32 = reinterpret_cast<const uint32_t *>(T);
   int mn = 0x7fffffff, mx = -0x7fffffff, bv = -1, bd = 0x7fffffff;
   ro.term_d = 0x7fffffff; ro.term_row = 0;
@@ -357,9 +358,9 @@ done:
 //  its descriptor (R2UR) from the call ABI's vector registers.
 template <int ILP>
 __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const uint64_t *T, int t0, int n,
-                        int error_limit, bool fwd_rules, unsigned long long *err_flags, int lane) {
+                        int error_limit, bool fwd_rules, unsigned long long *err_flags, int lane, int wib) {
   const DevParams &P = sh_params();
-  WarpCtl &C = sh_ctl();
+  WarpCtl &C = sh_ctl(wib);
   DpOut &o = C.o;                                    // every lane stores the same values
   unsigned int cells = 0;
   __syncwarp();                                      // every lane has read the previous extension's result
@@ -377,7 +378,7 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
   int pbase = 0;                                     // diagonal stored at index 2 of that ring
   uint32_t rcap = SRING;
   bool in_shared = true;
-  if (lane == 0) sh_ring(0)[2] = row0;
+  if (lane == 0) sh_ring(0, wib)[2] = row0;
   int L = 0, R = 0;
   int longest = 0, best_d = 0, best_e = 0;
   int ms_len = 0, ms_d = 0, ms_e = 0;
@@ -393,7 +394,7 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
     const int width = Ru - Lu + 1;
     if (in_shared && width + 4 > SRING) {            // migrate the previous row to the HBM ring
       int *g0 = psel ? C.gring1 : C.gring0;
-      const int *sp = sh_ring(psel);
+      const int *sp = sh_ring(psel, wib);
       for (int i = lane; i <= R - pbase + 4; i += 32) g0[i] = sp[i];
       __syncwarp();
       rcap = C.gring_cap; in_shared = false;
@@ -403,15 +404,18 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
       if (lane == 0) atomicOr(err_flags, 4ull);       // scratch too small: reported as an error by the host
       break;
     }
-    //  generic pointer (rare accesses only), biased so that prev[d] = EA[e-1][d]
-    int *prev = (in_shared ? sh_ring(psel) : (psel ? C.gring1 : C.gring0)) + (2 - pbase);
-    if (lane < 4) prev[lane < 2 ? L - 1 - lane : R - 1 + lane] = -2;      // sentinels at L-1, L-2, R+1, R+2: one store
+    //  sentinels at L-1, L-2, R+1, R+2: one store.  Shared and global rings are addressed in separate branches: a pointer
+    //  that may be either is a generic pointer, and forming one from a shared address costs special-register reads per row
+    if (lane < 4) {
+      const int si = (lane < 2 ? L - 1 - lane : R - 1 + lane) + 2 - pbase;
+      if (in_shared) sh_ring(psel, wib)[si] = -2; else (psel ? C.gring1 : C.gring0)[si] = -2;
+    }
     if (lane == 4) C.row_meta[e] = make_int2(Lu, (int)aoff);
     __syncwarp();
 
     RowOut ro;
-    if (in_shared) dp_row_cells<true, ILP>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
-    else           dp_row_cells<false, 1>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, ro);
+    if (in_shared) dp_row_cells<true, ILP>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, wib, ro);
+    else           dp_row_cells<false, 1>(psel, Lu - pbase + 1, A, a0, m, T, t0, n, Lu, Ru, ngroups, P.eml[e], C.arena + aoff, lane, wib, ro);
     const int term_d = ro.term_d, term_row = ro.term_row;
     int mn = ro.mn, mx = ro.mx; const int bv = ro.bv, bd = ro.bd;
     __syncwarp();
@@ -429,6 +433,8 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
       }
       if (abort_) break;                                // best-so-far result, assembled after the loop
       int d = term_d;
+      //  generic pointer (rare accesses only), biased so that prev[d] = EA[e-1][d]
+      const int *prev = (in_shared ? sh_ring(psel, wib) : (psel ? C.gring1 : C.gring0)) + (2 - pbase);
       if (fwd_rules && term_row == m && d < Ru && 1 + prev[d + 1] == term_row) {
         //  Force the last error to be a mismatch (forward.C:215-221): the path now starts in cell (e, d+1), which
         //  the DP never evaluated (it may lie in a 32-cell group after the one that terminated), so its from-code
@@ -483,9 +489,9 @@ __device__ OVL_DP_LINKAGE void warp_dp(const uint64_t *A, int a0, int m, const u
 template <int ILP>
 __device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
                                      int &s_lo, int &s_hi, int &t_lo, int &t_hi, int &errors, int &ldelta_len,
-                                     unsigned long long *err_flags, int lane) {
+                                     unsigned long long *err_flags, int lane, int wib) {
   const DevParams &P = sh_params();
-  WarpCtl &C = sh_ctl();
+  WarpCtl &C = sh_ctl(wib);
   int right_errors = 0, left_errors = 0, leftover = 0;
   bool r_to_end = true, l_to_end = true;
   const int S_len = C.s_len, T_len = C.t_len;
@@ -511,7 +517,7 @@ __device__ int warp_extend_alignment(int m_start, int m_offset, int m_len,
     const int s0 = right ? s_right_begin : S_len - 1 - s_left_begin, sl = right ? s_right_len : s_left_begin + 1;
     const int t0 = right ? t_right_begin : T_len - 1 - t_left_begin, tl = right ? t_right_len : t_left_begin + 1;
     warp_dp<ILP>(swap ? tw : sw, swap ? t0 : s0, swap ? tl : sl, swap ? sw : tw, swap ? s0 : t0, swap ? sl : tl,
-            right ? error_limit : error_limit - right_errors, right, err_flags, lane);
+            right ? error_limit : error_limit - right_errors, right, err_flags, lane, wib);
     const DpOut o = C.o;
     const int s_end = swap ? o.t_end : o.a_end, t_end = swap ? o.a_end : o.t_end;
     if (right) { right_errors = o.errors; s_hi = s_end; t_hi = t_end; r_to_end = o.match_to_end; rlen = o.delta_len; r_negate = !swap; }
@@ -667,8 +673,19 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, co
                const uint64_t *__restrict__ hfwd, const uint64_t *__restrict__ hrc, const uint64_t *__restrict__ hwoff,
                const uint32_t *__restrict__ hlen, uint32_t hash_first_id,
                ovlb_record *records, uint64_t rec_cap, unsigned long long *work, unsigned long long *counters) {
-  const int lane = threadIdx.x & 31;
-  const int gwarp = blockIdx.x * EXT_WARPS + (threadIdx.x >> 5);
+  int lane_ = threadIdx.x & 31;
+#ifndef OVL_EXT_NO_LANE_PIN
+  //  keep the lane number in a register: at 64 registers per thread the compiler otherwise re-reads SR_TID.X (S2R, a
+  //  slow special-register read) and masks it again at two dozen places inside the row loop (ncu: 3.3 % of the
+  //  kernel's instructions were attributed to this line)
+  asm volatile("" : "+r"(lane_));
+#endif
+  int wib_ = threadIdx.x >> 5;
+#ifndef OVL_EXT_NO_LANE_PIN
+  asm volatile("" : "+r"(wib_));
+#endif
+  const int lane = lane_, wib = wib_;
+  const int gwarp = blockIdx.x * EXT_WARPS + wib;
   bind_warp_ctl(P_, X, gwarp);
   if (gwarp >= X.n_warps) return;
   const DevParams &P = sh_params();
@@ -717,7 +734,7 @@ k_extend_pairs(DevParams P_, ExtScratch X, const PairRec *__restrict__ pairs, co
       const int m_start = seed_start[sb + li], m_offset = seed_off[sb + li], m_len = seed_len[sb + li];
 
       int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
-      const int kind = warp_extend_alignment<ILP>(m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len, err_flags, lane);
+      const int kind = warp_extend_alignment<ILP>(m_start, m_offset, m_len, s_lo, s_hi, t_lo, t_hi, errors, ld_len, err_flags, lane, wib);
 
       const bool usable = (kind == OVL_DOVETAIL) || P.partial;
       if (lane == 0 && usable && 1 + s_hi - s_lo >= P.min_olap_len && 1 + t_hi - t_lo >= P.min_olap_len) {
@@ -824,7 +841,7 @@ k_debug_extend(DevParams P_, ExtScratch X, uint32_t n, const uint32_t *__restric
     __syncwarp();
     int s_lo, s_hi, t_lo, t_hi, errors, ld_len;
     int kind = warp_extend_alignment<2>(m_start[i], m_offset[i], m_len[i], s_lo, s_hi, t_lo, t_hi, errors, ld_len,
-                                     &counters[CT_ERR_FLAGS], lane);
+                                     &counters[CT_ERR_FLAGS], lane, (int)(threadIdx.x >> 5));
     if (lane == 0) {
       int32_t *o = out7 + 7 * i;
       o[0] = s_lo; o[1] = s_hi; o[2] = t_lo; o[3] = t_hi; o[4] = errors; o[5] = kind; o[6] = ld_len;
