@@ -526,7 +526,7 @@ def main():
             "index_tuples_ms": ("k_part1 (k-mers -> tuples scattered into coarse partitions)", 1, hk * (0.5 + 16)),
             "index_sort_ms": ("k_part2 (coarse partition -> buckets, 8-byte tuples)", 1, hk * (16 + 8)),
             "index_table_ms": ("k_bucket_group2 (bulk-copy fed) + first-position bitmap + k_path_slots2", 1, hk * (8 + 4)),
-            "probe_ms": ("k_ref_probe", 1, rk * (0.5 + 32)),
+            "probe_ms": ("k_ref_probe<0> + k_ref_probe<1> (forward windows, then reverse windows)", 2, rk / 2 * (0.5 + 32)),
             "expand_ms": ("k_expand_coop", 1, sr * (4 + 16 + 16)),
             "sort_ms": ("radix sort of the seed runs", 8, sr * 16 * 2),
             "chain_ms": ("k_pair_scatter + k_chain_pairs", 1, sr * (16 + 12 + 12 + 16)),
@@ -539,7 +539,7 @@ def main():
             ach = ab / (ms_l * 1e-3) / 1e9
             stage_roof[st_name.replace("_ms", "")] = {"kernel": kname, "launches": nl, "ms_per_launch": round(ms_l, 4),
                                                       "achieved": round(ach, 1), "frac": round(ach / peaks["hbm_gbs"], 4)}
-        dom = max(stage_roof, key=lambda k2: stage_roof[k2]["ms_per_launch"])
+        dom = max(stage_roof, key=lambda k2: stage_roof[k2]["ms_per_launch"] * stage_roof[k2]["launches"])   # longest stage
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and args.hifi_genome == 5_000_000 and args.hifi_coverage == 50.0:
@@ -548,7 +548,8 @@ def main():
         roofline = {"bound": "hbm", "kernel": stage_roof[dom]["kernel"], "stage": dom, "achieved": stage_roof[dom]["achieved"],
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": stage_roof[dom]["frac"], "traffic": traffic, "peak_source": which,
                     "ms_per_launch": stage_roof[dom]["ms_per_launch"], "measured_on": "hifi_tile",
-                    "note": "longest HBM-bound kernel launch of the C2 tile; the job's dominant kernel (k_extend_pairs) is integer-ALU bound, see 'extension'"}
+                    "launches": stage_roof[dom]["launches"],
+                    "note": "longest HBM-bound stage of the C2 tile (bytes and time per launch); the job's dominant kernel (k_extend_pairs) is integer-ALU bound, see 'extension'"}
         line["hifi_tile"] = {
             "workload": "C2: %.1f Mbp x %gx HiFi-like reads (log-normal ~11 kb, %.1f%% read error), --maxerate %g, single hash x ref tile, inputs resident" % (
                 args.hifi_genome / 1e6, args.hifi_coverage, HIFI_READ_ERR * 100, HIFI_ERATE),
