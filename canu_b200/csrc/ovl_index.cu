@@ -1545,6 +1545,10 @@ k_expand_coop(ExpandArgs A, const uint4 *__restrict__ items_small, const unsigne
           //  the survivors are measured one after the other by the whole warp: have their first lines on the way
           asm volatile("prefetch.global.L1 [%0];" :: "l"(e.rw + ((e.p + A.K) >> 4)));
           asm volatile("prefetch.global.L1 [%0];" :: "l"(e.hw + ((e.q + A.K) >> 4)));
+          if (e.lim > 240) {                               // a 512-base step reads two 128-byte lines of either read
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(e.rw + ((e.p + A.K) >> 4) + 16));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(e.hw + ((e.q + A.K) >> 4) + 16));
+          }
           asm volatile("prefetch.global.L1 [%0];" :: "l"(A.ref_valid + (((uint64_t)dir * A.r_npos + pos_l) >> 5)));
         }
       }
