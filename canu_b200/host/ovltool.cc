@@ -13,7 +13,12 @@
 
 #include "ovfile.h"
 #include "ovstore.h"
+#include "prefetch.h"
 #include "sqstore.h"
+
+//  ovltool does not link the CUDA library: nothing it packs is ever page-locked, so Packed never calls these
+extern "C" int ovlb_host_register(const void *, size_t) { return 1; }
+extern "C" int ovlb_host_unregister(const void *) { return 0; }
 
 using namespace ovlhost;
 
@@ -160,6 +165,49 @@ int main(int argc, char **argv) {
     printf("%zu:%016lx%016lx\n", recs.size(), (unsigned long)s1, (unsigned long)s2);
     return 0;
   }
-  fprintf(stderr, "usage: ovltool write-store <sorted.bin> <out.ovlStore> <lastReadID> | lengths <seqStore> | hash-ovb <file.ovb> | dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID]\n");
+  if (argc >= 5 && !strcmp(argv[1], "prefetch-check")) {               // <seqStore> <pieces> <threads>: the multi-threaded prefetcher hands out the same batches, in plan order, as one thread
+    SqStore S;
+    if (!S.open(argv[2], err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    const uint32_t N = S.lastReadID(), pieces = std::max(1u, (uint32_t)strtoul(argv[3], nullptr, 10)), threads = std::max(1u, (uint32_t)strtoul(argv[4], nullptr, 10));
+    std::vector<PackItem> plan;
+    plan.push_back({true, 1, std::max(1u, N / 3)});                    // a hash block, then ref pieces of uneven size, an empty range, another block
+    for (uint32_t k = 0, b = 1; k < pieces && b <= N; k++) {
+      const uint32_t e = std::min(N, b + (N / pieces) * (1 + k % 3) / 2);
+      plan.push_back({false, b, e}); b = e + 1;
+      if (k == pieces / 2) { plan.push_back({false, 5, 4}); plan.push_back({true, N / 2 + 1, N}); }
+    }
+    auto digest = [](const Packed &P) {
+      uint64_t h = 1469598103934665603ull;
+      auto eat = [&h](const void *p, size_t n) { const uint8_t *b = (const uint8_t *)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+      eat(P.packed.data(), P.packed.size()); eat(P.boff.data(), P.boff.size() * 8); eat(P.len.data(), P.len.size() * 4);
+      eat(P.n_read.data(), P.n_read.size() * 4); eat(P.n_pos.data(), P.n_pos.size() * 4);
+      eat(P.src_len.data(), P.src_len.size() * 4); eat(P.clear_bgn.data(), P.clear_bgn.size() * 4); eat(&P.bases, 8);
+      eat(&P.view.n_reads, 4); eat(&P.view.first_read_id, 4);
+      return h;
+    };
+    auto run = [&](unsigned nt, std::vector<uint64_t> &out) -> bool {
+      Prefetcher pf(argv[2], plan, 0, 0xFFFFFFFFu, 0, 0xFFFFFFFFu, 500, nt > 1 ? 4 : 3, nt);
+      for (size_t i = 0; i < plan.size(); i++) {
+        std::unique_ptr<Packed> p = pf.next(err);
+        if (!p) return false;
+        if (p->view.n_reads && p->view.first_read_id != plan[i].bgn) { err = "batch out of plan order"; return false; }
+        out.push_back(digest(*p));
+        pf.recycle(std::move(p));                                        // recycled buffers must not leak a previous batch's contents
+      }
+      std::string e2;
+      if (pf.next(e2)) { err = "prefetcher handed out more than the plan"; return false; }
+      return true;
+    };
+    std::vector<uint64_t> one, many;
+    if (!run(1, one) || !run(threads, many)) { fprintf(stderr, "prefetch-check: %s\n", err.c_str()); return 1; }
+    uint64_t all = 0;
+    for (size_t i = 0; i < one.size(); i++) {
+      if (one[i] != many[i]) { fprintf(stderr, "prefetch-check: item %zu differs between 1 and %u threads\n", i, threads); return 1; }
+      all = all * 31 + one[i];
+    }
+    printf("prefetch-check ok: %zu items, %u threads, digest %016lx\n", one.size(), threads, (unsigned long)all);
+    return 0;
+  }
+  fprintf(stderr, "usage: ovltool write-store <sorted.bin> <out.ovlStore> <lastReadID> | lengths <seqStore> | hash-ovb <file.ovb> | dump-store <seqStore> [--packed] | dump-ovb <file.ovb> | rewrite-ovb <in.ovb> <out.ovb> <lastReadID> | pack-ovb <in.bin> <out.ovb> <lastReadID> | cmp-ovb <a.ovb> <b.ovb> [ignoreReadID] | prefetch-check <seqStore> <pieces> <threads>\n");
   return 1;
 }

@@ -89,3 +89,15 @@ def test_pack_ovb_roundtrip(tmp_path):
     oc = gu.read_oc(str(tmp_path / "out.oc"))
     want = np.bincount(recs["a_iid"], minlength=n_reads + 1) + np.bincount(recs["b_iid"], minlength=n_reads + 1)
     assert oc[0] == n and np.array_equal(np.asarray(oc[1])[: n_reads + 1], want[: n_reads + 1])
+
+
+@pytest.mark.parametrize("store", ["A", "B", "C"])
+@pytest.mark.parametrize("threads", [2, 5])
+def test_prefetcher_with_several_packers_hands_out_the_plan_in_order(store, threads):
+    """The executable's prefetcher (canu_b200/host/prefetch.h) packs the read ranges of a worker's plan ahead of the GPU, with
+    three packer threads on HiFi-like jobs.  `ovltool prefetch-check` walks a plan of hash blocks and uneven ref pieces
+    (one empty) with one packer and with several, recycling the buffers as the worker does: same batches, same order."""
+    r = subprocess.run([_tool(), "prefetch-check", os.path.join(gu.GOLDEN, store + ".seqStore"), "9", str(threads)], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout.decode().startswith("prefetch-check ok: 12 items, %d threads" % threads)
+
