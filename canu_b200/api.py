@@ -79,7 +79,7 @@ EXPORTS = [
     "ovlb_run_staged", "ovlb_stage_next_ref_batch", "ovlb_advance_staged", "ovlb_fetch_records", "ovlb_get_counters", "ovlb_reset_counters",
     "ovlb_get_timings", "ovlb_kernel_launches", "ovlb_timer_start", "ovlb_timer_stop", "ovlb_host_register", "ovlb_host_unregister", "ovlb_debug_pairs", "ovlb_debug_extend", "ovlb_debug_index_info", "ovlb_ingest_records",
     "ovlb_params_init", "ovlb_params_free", "ovlb_parse_erate", "ovlb_pack_reads", "ovlb_reads_view",
-    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_kmer_census", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_assign_tiles",
+    "ovlb_reads_free", "ovlb_kmer_keys", "ovlb_kmer_census", "ovlb_plan_tiles", "ovlb_plan_balanced", "ovlb_hash_block_bases", "ovlb_assign_tiles",
 ]
 
 
@@ -133,6 +133,8 @@ def load_library():
     L.ovlb_plan_tiles.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
                                   C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.ovlb_assign_tiles.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    L.ovlb_hash_block_bases.restype = C.c_uint64
+    L.ovlb_hash_block_bases.argtypes = [C.c_uint64, C.c_uint32, C.c_double, C.c_uint64]
     L.ovlb_plan_balanced.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_double, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     _LIB = L
@@ -434,6 +436,11 @@ def plan_tiles(read_lens, min_olap_len, hash_block_len, ref_block_len, hash_rang
     _check(L.ovlb_plan_tiles(rl.ctypes.data, n, min_olap_len, hash_block_len, ref_block_len, hb, he, rb, re_,
                              int(strict_reference), C.cast(arr, C.c_void_p), cnt.value, C.byref(cnt)))
     return [{f: getattr(arr[i], f) for f, _ in _Tile._fields_} for i in range(cnt.value)]
+
+
+def hash_block_bases(budget_bytes, max_read_len, max_erate, ref_batch_bases=256_000_000):
+    """Bases of hash reads one context with `budget_bytes` of device memory can index (ovlb_hash_block_bases)."""
+    return int(load_library().ovlb_hash_block_bases(int(budget_bytes), int(max_read_len), float(max_erate), int(ref_batch_bases)))
 
 
 def plan_balanced(read_lens, min_olap_len, n_parts, hash_range=None, ref_range=None, lookup_weight=0.002):

@@ -249,6 +249,20 @@ int ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ola
   return OVLB_OK;
 }
 
+//  Hash-block size from a context's memory budget (the executable's re-blocking; include/ovlb200.h states the model).
+//  The run-side terms follow the allocations they stand for: run buffers mem_budget / 12 (ovl_seed_ref_batch), extension
+//  scratch per warp = from-code arena (sum over rows of ceil((2e + 1) / 32) words of 8 bytes) + HBM rings + per-row arrays
+//  for 148 x 32 warps, at most mem_budget / 4 (ovl_prepare_ext_scratch).
+uint64_t ovlb_hash_block_bases(uint64_t budget_bytes, uint32_t max_read_len, double max_erate, uint64_t ref_batch_bases) {
+  const double em = max_erate * (double)max_read_len + 64;              // rows of the longest extension
+  const double per_warp = (em * em / 32 + em) * 8 + em * 64 + 4096;
+  uint64_t run_side = budget_bytes / 12;
+  run_side += (uint64_t)std::min<double>((double)budget_bytes / 4, 1.3 * per_warp * 148 * 32);
+  run_side += 2 * 3 * ref_batch_bases + (3ull << 30);                   // two ref slots (dp4 both strands, groups, hit words), records, slack
+  const uint64_t block_side = budget_bytes > run_side ? (uint64_t)((double)(budget_bytes - run_side) * 0.9) : 0;
+  return std::min<uint64_t>(1500000000ull, std::max<uint64_t>(block_side / 150, 1000000ull));
+}
+
 //  Cost-balanced cut of one hash block's ref range ("when #hash blocks < #GPUs replicate the hash block on
 //  every GPU and split the REF RANGE N ways").  Only refID < hashID pairs are computed (Find_Overlaps.C:279,320), so a ref
 //  read meets only the hash reads behind it: the work of ref read r is ~ len_r x (hash bases with ID > r), a triangle,

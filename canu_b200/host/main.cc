@@ -299,16 +299,8 @@ int main(int argc, char **argv) {
     minBudget = std::min<uint64_t>(minBudget, (uint64_t)((double)tot * 0.95 * 0.8 / sharers[wi]));
   }
   const uint64_t refBatchDefault = 256000000ull;
-  uint64_t runSide = minBudget / 12;
-  {
-    const double em = G.maxErate * (double)maxLen + 64;                  // rows of the longest extension
-    const double perWarp = (em * em / 32 + em) * 8 + em * 64 + 4096;     // from-code arena + HBM rings + per-row arrays
-    runSide += (uint64_t)std::min<double>((double)minBudget / 4, 1.3 * perWarp * 148 * 32);
-    runSide += 2 * 3 * (G.refBatchBases ? G.refBatchBases : refBatchDefault) + (3ull << 30);   // two ref slots (dp4 both strands, groups, hit words), records, slack
-  }
-  const uint64_t blockSide = minBudget > runSide ? (uint64_t)((double)(minBudget - runSide) * 0.9) : 0;
-  const uint64_t hashBlockModel = std::max<uint64_t>(blockSide / 150, 1000000ull);
-  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases : std::min<uint64_t>(1500000000ull, hashBlockModel);
+  const uint64_t hashBlock = G.hashBlockBases ? G.hashBlockBases
+                                              : ovlb_hash_block_bases(minBudget, maxLen, G.maxErate, G.refBatchBases ? G.refBatchBases : refBatchDefault);
   uint64_t refBatch = G.refBatchBases ? G.refBatchBases : refBatchDefault;
   //  Several workers: every one should get a few tiles of each hash block so that longest-first assignment can balance
   //  them, but not many small ones -- an extension launch cannot end before its slowest pair does (0.2 - 1 s on noisy

@@ -283,6 +283,14 @@ int  ovlb_plan_tiles(const uint32_t *read_len, uint32_t n_reads, uint32_t min_ol
                      uint64_t hash_block_len, uint64_t ref_block_len,
                      uint32_t hash_min, uint32_t hash_max, uint32_t ref_min, uint32_t ref_max,
                      int strict_reference, ovlb_tile *out, uint64_t out_cap, uint64_t *n_out);
+/*  Bases of hash reads one context can index: the re-blocking counterpart of Canu's ovlHashBlockLength
+ *  (pipelines/canu/Configure.pm:585-602 picks it from the host's memory per job; here it comes from the device's).
+ *  budget_bytes = the memory the context may use.  Taken off first: the seed-run buffers (1/12 of the budget), the
+ *  extension scratch (from the longest read and the error rate, at most 1/4), two ref slots of ref_batch_bases, records
+ *  and slack; 90 % of the rest at 150 B per hash base (1 B of dp4 reads, ~40 B of tuple scratch, ~100 B per distinct
+ *  k-mer -- a large job's blocks are mostly distinct k-mers).  Clamped to [1 Mbase, 1.5 Gbases].  */
+uint64_t ovlb_hash_block_bases(uint64_t budget_bytes, uint32_t max_read_len, double max_erate, uint64_t ref_batch_bases);
+
 /*  Cost-balanced cut of ONE hash block's ref range into n_parts contiguous tiles (at most; fewer when the range holds
  *  fewer reads).  Only refID < hashID pairs are computed (overlapInCore-Find_Overlaps.C:279,320), so the work of ref read r
  *  is ~ len_r x (hash bases with ID > r); equal-base blocks (overlapInCorePartition.C:204-226) are unequal work.  Used

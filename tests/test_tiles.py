@@ -110,3 +110,24 @@ def test_balanced_ref_cut_subranges_and_degenerate():
     assert api.plan_balanced(lens, 500, 4, hash_range=(5, 5), ref_range=(5, 9)) == []
     few = api.plan_balanced(lens, 500, 8, hash_range=(1, 4), ref_range=(1, 4))
     assert 1 <= len(few) <= 3 and few[-1]["ref_end"] == 3
+
+
+def test_hash_block_model_follows_the_memory_budget():
+    """ovlb_hash_block_bases: the re-blocking counterpart of Configure.pm's ovlHashBlockLength.  What the run side needs
+    comes off the budget first, the rest is divided by 150 B per hash base: 734 Mbases for the 0.76 x 183 GB a context
+    gets on a B200 (HiFi-like job), less when long noisy reads need a large extension scratch or the ref batches are
+    larger, half of it (and a bit) for two contexts on one device; clamped to [1 Mbase, 1.5 Gbases]."""
+    from canu_b200 import api
+    b200 = int(183e9 * 0.95 * 0.8)
+    hifi = api.hash_block_bases(b200, 30000, 0.01)
+    assert 720e6 < hifi < 750e6
+    noisy = api.hash_block_bases(b200, 60000, 0.12)
+    assert noisy < api.hash_block_bases(b200, 20000, 0.06) < hifi
+    assert api.hash_block_bases(b200, 30000, 0.01, ref_batch_bases=1_000_000_000) < hifi
+    half = api.hash_block_bases(b200 // 2, 30000, 0.01)
+    assert 0.4 * hifi < half < 0.5 * hifi
+    assert api.hash_block_bases(10 ** 9, 30000, 0.01) == 1_000_000                # too little memory: the floor
+    assert api.hash_block_bases(10 ** 13, 30000, 0.01) == 1_500_000_000           # the 2^32-position cap of one block
+    grown = [api.hash_block_bases(g << 30, 30000, 0.01) for g in range(8, 200, 8)]
+    assert grown == sorted(grown)
+
