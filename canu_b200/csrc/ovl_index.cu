@@ -2032,6 +2032,10 @@ int ovl_build_index(ovlb_ctx *c) {
   const uint64_t nd = X.n_distinct, ns = nd + skip.size();
   if (ns >= 0xFFFFFFF0ull) { ovl_set_error("too many distinct k-mers for one index (>= 2^32); use a smaller hash block"); return OVLB_ERR_CAPACITY; }
   uint64_t hcap = (4 * ns + 64) & ~3ull;                   // 8-byte entries in buckets of four, a quarter of them used
+  if (const char *ev = getenv("OVLB_HT_PERCENT")) {        // tests: a table filled to `percent` (e.g. 90) makes most buckets overflow into the next ones
+    const long pc = atol(ev);
+    if (pc >= 25 && pc <= 98) hcap = (ns * 100 / (uint64_t)pc + 8) & ~3ull;
+  }
   if ((rc = ensure(X.slots, X.slots_cap, (size_t)ns + 1, 9, 8))) return rc;
   if (!tmp_ready) {
     if ((rc = ensure(X.tmp_slots, X.tmp_cap, (size_t)nd + 1, 9, 8))) return rc;

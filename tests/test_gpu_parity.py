@@ -433,13 +433,20 @@ def test_hash_table_fingerprint_collisions_are_resolved_by_the_slot(monkeypatch,
         return a, c
 
     want, cw = run()
-    monkeypatch.setenv("OVLB_HT_FPMASK", "0x3")
-    got, cg = run()
-    assert len(want) > 100 and len(got) == len(want)
-    for f in ("a_iid", "b_iid", "w0", "w1"):
-        assert np.array_equal(got[f], want[f]), f
     drop = ("ext_busy_ns", "ext_capacity_ns")
-    assert {k: v for k, v in cg.items() if k not in drop} == {k: v for k, v in cw.items() if k not in drop}
+    #  2-bit fingerprints; then a table filled to 92 % (hook OVLB_HT_PERCENT: nearly every bucket is full, keys sit several
+    #  buckets past their home, a k-mer and its reverse complement in different buckets, the probe sequence wraps around the
+    #  end of the table) -- the lookups, and what the forward pass tells the reverse pass not to look up, must not change
+    for env in ({"OVLB_HT_FPMASK": "0x3"}, {"OVLB_HT_PERCENT": "92"}, {"OVLB_HT_FPMASK": "0x1", "OVLB_HT_PERCENT": "97"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, cg = run()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert len(want) > 100 and len(got) == len(want), env
+        for f in ("a_iid", "b_iid", "w0", "w1"):
+            assert np.array_equal(got[f], want[f]), (env, f)
+        assert {k: v for k, v in cg.items() if k not in drop} == {k: v for k, v in cw.items() if k not in drop}, env
 
 
 @pytest.mark.parametrize("homopoly", [False, True])
